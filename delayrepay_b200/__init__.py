@@ -1,0 +1,15 @@
+"""delayrepay_b200 -- a B200-native lazy-evaluation array engine behind DelayRepay's drop-in
+NumPy API (reference delayrepay/__init__.py:4-17).  ``import delayrepay_b200 as np`` (or the
+alias package ``import delayrepay as np``).
+"""
+from . import backend                       # noqa: F401
+from .delayarray import *                   # noqa: F401,F403
+from .delayarray import (DelayArray, NPArray, Scalar, BinaryNumpyEx, UnaryFuncEx,  # noqa: F401
+                         BinaryFuncEx, ReduceEx, DotEx, MVEx, MMEx, NPRef, Memoiser, reset, cast,
+                         evaluate, implements, HANDLED_FUNCTIONS, sum, max, min, abs)
+from .device import (DeviceArray, set_device, current_device, synchronize,  # noqa: F401
+                     pinned_empty)
+from . import random, fft                   # noqa: F401
+
+pi = backend.backend.np.pi
+__version__ = "0.1.0"

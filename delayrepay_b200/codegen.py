@@ -1,0 +1,449 @@
+"""CUDA C++ code generator: one kernel per fused region (replaces CupyEmitter/make_kernel,
+reference cuda.py:35-88, which builds a `T name = expr` statement list for
+cupy.ElementwiseKernel).
+
+Kernel families
+  flat      one contiguous dimension: 128-bit vector loads/stores (ld.global.nc.L1::no_allocate /
+            st.global.cs), U independent vectors in flight per thread, grid-stride, scalar tail
+  nd        general strided / broadcast operands: index decomposition, coalesced scalar accesses
+  *+reduce  either family with a fused full reduction: per-thread accumulators -> warp shuffle
+            -> shared memory -> one partial per block -> deterministic last-block finish
+  rows      reduction over the trailing axis of a (rows, cols) iteration space (sum(axis=-1),
+            matrix @ vector): one warp or one block per row, fused producer
+Everything is emitted with positional names so equal structure == equal source text.
+"""
+import numpy as np
+
+CTYPE = {
+    "?": "bool", "b": "signed char", "B": "unsigned char", "h": "short", "H": "unsigned short",
+    "i": "int", "I": "unsigned int", "l": "long long", "L": "unsigned long long",
+    "q": "long long", "Q": "unsigned long long", "f": "float", "d": "double",
+}
+
+
+def ctype(dt):
+    return CTYPE[np.dtype(dt).char]
+
+
+def _lit(dt, v):
+    dt = np.dtype(dt)
+    if dt.kind == "f":
+        return f"(({ctype(dt)}){float(v)!r})".replace("inf", "DR_INF").replace("nan", "DR_NAN")
+    return f"(({ctype(dt)}){int(v)})"
+
+
+_INFIX = {"add": "+", "subtract": "-", "multiply": "*", "true_divide": "/", "divide": "/",
+          "greater": ">", "greater_equal": ">=", "less": "<", "less_equal": "<=",
+          "equal": "==", "not_equal": "!=", "bitwise_and": "&", "bitwise_or": "|",
+          "bitwise_xor": "^", "left_shift": "<<", "right_shift": ">>"}
+_CALL1 = {"sqrt", "exp", "exp2", "expm1", "log", "log2", "log10", "log1p", "sin", "cos", "tan",
+          "sinh", "cosh", "tanh", "cbrt", "erf", "erfc", "floor", "ceil", "trunc", "rint",
+          "sign", "isnan", "isinf", "isfinite", "signbit"}
+_CALL1_RENAMED = {"arcsin": "asin", "arccos": "acos", "arctan": "atan", "arcsinh": "asinh",
+                  "arccosh": "acosh", "arctanh": "atanh", "absolute": "abs", "fabs": "abs"}
+_CALL2 = {"hypot", "copysign", "fmod", "fmax", "fmin", "remainder", "floor_divide"}
+_CALL2_RENAMED = {"arctan2": "atan2", "maximum": "max", "minimum": "min"}
+
+
+def emit_expr(op, loop, out_dt, args, arg_dts):
+    """C expression for one SSA instruction; ``args`` are C expressions of dtype arg_dts."""
+    cast_args = []
+    for a, have, want in zip(args, arg_dts, loop):
+        if have == want:
+            cast_args.append(a)
+        elif want.kind == "b":
+            cast_args.append(f"({a} != 0)")
+        else:
+            cast_args.append(f"(({ctype(want)})({a}))")
+    a = cast_args
+    T = ctype(loop[0])
+    k = loop[0].kind
+    O = ctype(out_dt)
+    if op == "cast":
+        return f"({a[0]} != 0)" if out_dt.kind == "b" else f"(({O})({a[0]}))"
+    if op == "where":
+        return f"({a[0]} ? {a[1]} : {a[2]})"
+    if k == "b" and op in ("add", "maximum", "bitwise_or", "logical_or"):
+        return f"({a[0]} || {a[1]})"
+    if k == "b" and op in ("multiply", "minimum", "bitwise_and", "logical_and"):
+        return f"({a[0]} && {a[1]})"
+    if k == "b" and op in ("bitwise_xor", "logical_xor", "not_equal"):
+        return f"({a[0]} != {a[1]})"
+    if op in ("true_divide", "divide") and k in "iu":       # never produced by NumPy's resolver
+        raise TypeError("integer true_divide")
+    if op in _INFIX:
+        e = f"({a[0]} {_INFIX[op]} {a[1]})"
+        return e if out_dt.kind == "b" else f"(({O}){e})"
+    if op == "negative":
+        return f"(({O})(-{a[0]}))"
+    if op == "positive":
+        return a[0]
+    if op == "reciprocal":
+        return f"(({O})(({T})1 / {a[0]}))"
+    if op == "logical_and":
+        return f"(({a[0]} != 0) && ({a[1]} != 0))"
+    if op == "logical_or":
+        return f"(({a[0]} != 0) || ({a[1]} != 0))"
+    if op == "logical_xor":
+        return f"(({a[0]} != 0) != ({a[1]} != 0))"
+    if op == "logical_not":
+        return f"({a[0]} == 0)"
+    if op == "invert":
+        return f"(!{a[0]})" if k == "b" else f"(({O})(~{a[0]}))"
+    if op == "power":
+        return f"dr_pow({a[0]}, {a[1]})" if k == "f" else f"dr_ipow<{T}>({a[0]}, {a[1]})"
+    if op in ("deg2rad", "radians"):
+        return f"({a[0]} * (({T})0.017453292519943295))"
+    if op in ("rad2deg", "degrees"):
+        return f"({a[0]} * (({T})57.29577951308232))"
+    if op in _CALL1:
+        return f"dr_{op}({a[0]})"
+    if op in _CALL1_RENAMED:
+        return f"dr_{_CALL1_RENAMED[op]}({a[0]})"
+    if op in _CALL2:
+        return f"dr_{op}<{T}>({a[0]}, {a[1]})" if k != "f" or op in ("fmax", "fmin") \
+            else f"dr_{op}({a[0]}, {a[1]})"
+    if op in _CALL2_RENAMED:
+        fn = _CALL2_RENAMED[op]
+        return f"dr_{fn}({a[0]}, {a[1]})" if fn == "atan2" else f"dr_{fn}<{T}>({a[0]}, {a[1]})"
+    raise KeyError(op)
+
+
+def _operand_name(ref):
+    return {"a": "x", "s": "s", "t": "t"}[ref[0]] + str(ref[1])
+
+
+def emit_body(prog):
+    """The fused scalar body: `const T tK = expr;` lines over x<i> (arrays), s<j> (scalars)."""
+    lines = []
+    for k, (op, loop, out_dt, args) in enumerate(prog.instrs):
+        exprs = [_operand_name(r) for r in args]
+        dts = [prog.dtypes[r] for r in args]
+        lines.append(f"const {ctype(out_dt)} t{k} = {emit_expr(op, loop, out_dt, exprs, dts)};")
+    return lines
+
+
+# --------------------------------------------------------------------------- reductions
+_RED = {"sum": "DrSum", "prod": "DrProd", "max": "DrMax", "min": "DrMin"}
+
+
+def acc_dtype(op, dt):
+    """Accumulator type: float32 sums accumulate in double (error far below rtol 1e-5 at 2^30
+    elements); everything else accumulates in its own type."""
+    dt = np.dtype(dt)
+    if op in ("sum", "prod") and dt == np.float32:
+        return np.dtype(np.float64)
+    return dt
+
+
+def _identity(op, dt):
+    dt = np.dtype(dt)
+    c = ctype(dt)
+    if op == "sum":
+        return f"(({c})0)"
+    if op == "prod":
+        return f"(({c})1)"
+    if dt.kind == "f":
+        return f"(({c})(-DR_INF))" if op == "max" else f"(({c})DR_INF)"
+    if dt.kind == "b":
+        return "false" if op == "max" else "true"
+    info = np.iinfo(dt)
+    v = info.min if op == "max" else info.max
+    if dt.kind == "i" and dt.itemsize == 8 and op == "max":
+        return "((long long)(-9223372036854775807LL - 1))"
+    suffix = "ULL" if dt.kind == "u" and dt.itemsize == 8 else ("LL" if dt.itemsize == 8 else "")
+    return f"(({c}){v}{suffix})"
+
+
+# --------------------------------------------------------------------------- flat family
+def gen_flat(name, prog, in_class, out_dts, vec_ok, stream, reduce=None, unroll=None,
+             threads=256, min_blocks=None):
+    """Contiguous 1-d kernel.  ``reduce`` = None or (op, acc np.dtype, result np.dtype, post)."""
+    arrays, scalars = prog.arrays, prog.scalars
+    n_in = len(arrays)
+    item_sizes = [a.dtype.itemsize for a, c in zip(arrays, in_class) if c == "c"]
+    item_sizes += [np.dtype(d).itemsize for d in out_dts] if reduce is None else []
+    widest = max(item_sizes) if item_sizes else 4
+    V = max(1, 16 // widest) if vec_ok else 1
+    n_stream = sum(1 for c in in_class if c == "c") + (len(out_dts) if reduce is None else 0)
+    if unroll is None:
+        unroll = 4 if n_stream <= 2 else (2 if n_stream <= 6 else 1)
+    U = unroll
+    S = "true" if stream else "false"
+
+    params = ["const i64 n"]
+    for i, a in enumerate(arrays):
+        params.append(f"const {ctype(a.dtype)}* __restrict__ in{i}")
+    for j, (_, dt) in enumerate(scalars):
+        params.append(f"const {ctype(dt)} s{j}")
+    if reduce is None:
+        for o, dt in enumerate(out_dts):
+            params.append(f"{ctype(dt)}* __restrict__ out{o}")
+    else:
+        rop, acc_dt, res_dt, post = reduce
+        A = ctype(acc_dt)
+        params += [f"{A}* __restrict__ partials", "unsigned int* __restrict__ counter",
+                   f"{ctype(res_dt)}* __restrict__ result", "const double post_scale"]
+
+    body = emit_body(prog)
+    src = []
+    w = src.append
+    lb = f"__launch_bounds__({threads}" + (f", {min_blocks})" if min_blocks else ")")
+    w(f'extern "C" __global__ void {lb} {name}({", ".join(params)}) {{')
+    for i, (a, c) in enumerate(zip(arrays, in_class)):
+        if c == "b":
+            w(f"  const {ctype(a.dtype)} x{i} = in{i}[0];")
+    if reduce is not None:
+        w(f"  {A} acc[{U}];")
+        w(f"#pragma unroll\n  for (int u = 0; u < {U}; ++u) acc[u] = {_identity(rop, acc_dt)};")
+    w(f"  const i64 nv = n / {V};")
+    w("  const i64 stride = (i64)gridDim.x * blockDim.x;")
+    w("  i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;")
+
+    def trip(u_count, indent):
+        p = " " * indent
+        for i, (a, c) in enumerate(zip(arrays, in_class)):
+            if c == "c":
+                w(f"{p}Vec<{ctype(a.dtype)}, {V}> v{i}[{u_count}];")
+        w(f"{p}#pragma unroll")
+        w(f"{p}for (int u = 0; u < {u_count}; ++u) {{")
+        for i, (a, c) in enumerate(zip(arrays, in_class)):
+            if c == "c":
+                w(f"{p}  v{i}[u] = dr_ld<{S}, {ctype(a.dtype)}, {V}>(in{i} + (i + u * stride) * {V});")
+        w(f"{p}}}")
+        w(f"{p}#pragma unroll")
+        w(f"{p}for (int u = 0; u < {u_count}; ++u) {{")
+        if reduce is None:
+            for o, dt in enumerate(out_dts):
+                w(f"{p}  Vec<{ctype(dt)}, {V}> r{o};")
+        w(f"{p}  #pragma unroll")
+        w(f"{p}  for (int e = 0; e < {V}; ++e) {{")
+        for i, (a, c) in enumerate(zip(arrays, in_class)):
+            if c == "c":
+                w(f"{p}    const {ctype(a.dtype)} x{i} = v{i}[u].v[e];")
+        for line in body:
+            w(f"{p}    {line}")
+        if reduce is None:
+            for o, (r, dt) in enumerate(zip(prog.roots, out_dts)):
+                w(f"{p}    r{o}.v[e] = {_store_expr(prog, r, dt)};")
+        else:
+            w(f"{p}    acc[u] = {_RED[rop]}::op(acc[u], ({A}){_operand_name(prog.roots[0])});")
+        w(f"{p}  }}")
+        if reduce is None:
+            for o, dt in enumerate(out_dts):
+                w(f"{p}  dr_st<{S}, {ctype(dt)}, {V}>(out{o} + (i + u * stride) * {V}, r{o});")
+        w(f"{p}}}")
+
+    if U > 1:
+        w(f"  for (; i + {U - 1} * stride < nv; i += {U} * stride) {{")
+        trip(U, 4)
+        w("  }")
+    w("  for (; i < nv; i += stride) {")
+    trip(1, 4)
+    w("  }")
+    # scalar tail: n - nv*V < V elements, handled by the first threads of block 0
+    if V > 1:
+        w(f"  if (blockIdx.x == 0 && threadIdx.x < (unsigned)(n - nv * {V})) {{")
+        w(f"    const i64 j = nv * {V} + threadIdx.x;")
+        for i, (a, c) in enumerate(zip(arrays, in_class)):
+            if c == "c":
+                w(f"    const {ctype(a.dtype)} x{i} = in{i}[j];")
+        for line in body:
+            w(f"    {line}")
+        if reduce is None:
+            for o, (r, dt) in enumerate(zip(prog.roots, out_dts)):
+                w(f"    out{o}[j] = {_store_expr(prog, r, dt)};")
+        else:
+            w(f"    acc[0] = {_RED[rop]}::op(acc[0], ({A}){_operand_name(prog.roots[0])});")
+        w("  }")
+    if reduce is not None:
+        _emit_reduce_finish(w, rop, acc_dt, res_dt, U)
+    w("}")
+    return "\n".join(src) + "\n"
+
+
+def _store_expr(prog, ref, out_dt):
+    have = prog.dtypes[ref]
+    nm = _operand_name(ref)
+    if have == out_dt:
+        return nm
+    if np.dtype(out_dt).kind == "b":
+        return f"({nm} != 0)"
+    return f"(({ctype(out_dt)})({nm}))"
+
+
+def _emit_reduce_finish(w, rop, acc_dt, res_dt, U):
+    A = ctype(acc_dt)
+    ident = _identity(rop, acc_dt)
+    w(f"  {A} total = acc[0];")
+    if U > 1:
+        w(f"#pragma unroll\n  for (int u = 1; u < {U}; ++u) total = {_RED[rop]}::op(total, acc[u]);")
+    w(f"  __shared__ {A} scratch[32];")
+    w(f"  total = dr_block_reduce<{_RED[rop]}>(total, {ident}, scratch);")
+    w(f"  __shared__ {A} final_value;")
+    w(f"  if (dr_grid_reduce<{_RED[rop]}>(total, {ident}, partials, counter, scratch, &final_value)) {{")
+    if np.dtype(acc_dt).kind == "f":
+        w(f"    *result = ({ctype(res_dt)})(final_value / ({A})post_scale);")
+    else:
+        w(f"    *result = ({ctype(res_dt)})final_value;")
+    w("  }")
+
+
+# --------------------------------------------------------------------------- nd family
+def gen_nd(name, prog, ndim, in_class, out_dts, reduce=None, threads=256, wide_index=False):
+    """General strided/broadcast kernel.  Geometry arrives in one struct argument:
+    shape[ndim], then byte strides per operand per dim (inputs then outputs)."""
+    arrays, scalars = prog.arrays, prog.scalars
+    n_ops = len(arrays) + (len(out_dts) if reduce is None else 0)
+    I = "i64" if wide_index else "u32"
+    src = []
+    w = src.append
+    w(f"struct Geo_{name} {{ i64 total; i64 shape[{ndim}]; i64 stride[{max(n_ops, 1)}][{ndim}]; }};")
+    params = [f"const Geo_{name} g"]
+    for i, a in enumerate(arrays):
+        params.append(f"const char* __restrict__ in{i}")
+    for j, (_, dt) in enumerate(scalars):
+        params.append(f"const {ctype(dt)} s{j}")
+    if reduce is None:
+        for o, dt in enumerate(out_dts):
+            params.append(f"char* __restrict__ out{o}")
+    else:
+        rop, acc_dt, res_dt, post = reduce
+        A = ctype(acc_dt)
+        params += [f"{A}* __restrict__ partials", "unsigned int* __restrict__ counter",
+                   f"{ctype(res_dt)}* __restrict__ result", "const double post_scale"]
+    body = emit_body(prog)
+    w(f'extern "C" __global__ void __launch_bounds__({threads}) {name}({", ".join(params)}) {{')
+    for i, (a, c) in enumerate(zip(arrays, in_class)):
+        if c == "b":
+            w(f"  const {ctype(a.dtype)} x{i} = *reinterpret_cast<const {ctype(a.dtype)}*>(in{i});")
+    if reduce is not None:
+        w(f"  {A} acc[1]; acc[0] = {_identity(rop, acc_dt)};")
+    w(f"  const {I} total = ({I})g.total;")
+    w(f"  const {I} step = ({I})gridDim.x * blockDim.x;")
+    w(f"  for ({I} idx = ({I})blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += step) {{")
+    w(f"    {I} rem = idx;")
+    w(f"    i64 off[{max(n_ops, 1)}];")
+    w(f"#pragma unroll\n    for (int k = 0; k < {max(n_ops, 1)}; ++k) off[k] = 0;")
+    w(f"#pragma unroll\n    for (int d = {ndim - 1}; d >= 0; --d) {{")
+    w(f"      const {I} extent = ({I})g.shape[d];")
+    w(f"      const {I} q = d ? rem / extent : 0;")
+    w(f"      const {I} c = d ? rem - q * extent : rem;")
+    w("      rem = q;")
+    w(f"#pragma unroll\n      for (int k = 0; k < {max(n_ops, 1)}; ++k) off[k] += (i64)c * g.stride[k][d];")
+    w("    }")
+    for i, (a, c) in enumerate(zip(arrays, in_class)):
+        if c != "b":
+            w(f"    const {ctype(a.dtype)} x{i} = *reinterpret_cast<const {ctype(a.dtype)}*>(in{i} + off[{i}]);")
+    for line in body:
+        w(f"    {line}")
+    if reduce is None:
+        for o, (r, dt) in enumerate(zip(prog.roots, out_dts)):
+            w(f"    *reinterpret_cast<{ctype(dt)}*>(out{o} + off[{len(arrays) + o}]) = {_store_expr(prog, r, dt)};")
+    else:
+        w(f"    acc[0] = {_RED[rop]}::op(acc[0], ({A}){_operand_name(prog.roots[0])});")
+    w("  }")
+    if reduce is not None:
+        _emit_reduce_finish(w, rop, acc_dt, res_dt, 1)
+    w("}")
+    return "\n".join(src) + "\n"
+
+
+# --------------------------------------------------------------------------- rows family
+def gen_rows(name, prog, in_class, reduce, mode, threads=256):
+    """Reduce the trailing axis of a (rows, cols) space.  Geometry per operand: byte stride
+    along rows and along cols (either may be 0 = broadcast).  mode 'warp': one warp per row
+    (short rows), 'block': one block per row (long rows)."""
+    arrays, scalars = prog.arrays, prog.scalars
+    rop, acc_dt, res_dt, post = reduce
+    A = ctype(acc_dt)
+    n_ops = max(len(arrays), 1)
+    src = []
+    w = src.append
+    w(f"struct Geo_{name} {{ i64 rows; i64 cols; i64 rs[{n_ops}]; i64 cs[{n_ops}]; i64 out_stride; }};")
+    params = [f"const Geo_{name} g"]
+    for i, a in enumerate(arrays):
+        params.append(f"const char* __restrict__ in{i}")
+    for j, (_, dt) in enumerate(scalars):
+        params.append(f"const {ctype(dt)} s{j}")
+    params += ["char* __restrict__ result", "const double post_scale"]
+    body = emit_body(prog)
+    w(f'extern "C" __global__ void __launch_bounds__({threads}) {name}({", ".join(params)}) {{')
+    for i, (a, c) in enumerate(zip(arrays, in_class)):
+        if c == "b":
+            w(f"  const {ctype(a.dtype)} x{i} = *reinterpret_cast<const {ctype(a.dtype)}*>(in{i});")
+    if mode == "warp":
+        w("  const int lanes = 32;")
+        w("  const i64 row0 = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;")
+        w("  const i64 row_step = ((i64)gridDim.x * blockDim.x) >> 5;")
+        w("  const int lane = threadIdx.x & 31;")
+    else:
+        w("  const int lanes = blockDim.x;")
+        w("  const i64 row0 = blockIdx.x;")
+        w("  const i64 row_step = gridDim.x;")
+        w("  const int lane = threadIdx.x;")
+        w(f"  __shared__ {A} scratch[32];")
+    w("  for (i64 r = row0; r < g.rows; r += row_step) {")
+    w(f"    {A} acc = {_identity(rop, acc_dt)};")
+    w("    for (i64 c = lane; c < g.cols; c += lanes) {")
+    for i, (a, c) in enumerate(zip(arrays, in_class)):
+        if c != "b":
+            w(f"      const {ctype(a.dtype)} x{i} = *reinterpret_cast<const {ctype(a.dtype)}*>"
+              f"(in{i} + r * g.rs[{i}] + c * g.cs[{i}]);")
+    for line in body:
+        w(f"      {line}")
+    w(f"      acc = {_RED[rop]}::op(acc, ({A}){_operand_name(prog.roots[0])});")
+    w("    }")
+    if mode == "warp":
+        w(f"    acc = dr_warp_reduce<{_RED[rop]}>(acc);")
+    else:
+        w(f"    acc = dr_block_reduce<{_RED[rop]}>(acc, {_identity(rop, acc_dt)}, scratch);")
+    fin = f"({ctype(res_dt)})(acc / ({A})post_scale)" if np.dtype(acc_dt).kind == "f" \
+        else f"({ctype(res_dt)})acc"
+    w(f"    if (lane == 0) *reinterpret_cast<{ctype(res_dt)}*>(result + r * g.out_stride) = {fin};")
+    w("  }")
+    w("}")
+    return "\n".join(src) + "\n"
+
+
+# --------------------------------------------------------------------------- cols family
+def gen_cols(name, prog, in_class, reduce, threads=256):
+    """Reduce the MIDDLE axis of an (outer, red, inner) space with inner > 1: one thread per
+    (outer, inner) output element, coalesced along inner, serial over red."""
+    arrays, scalars = prog.arrays, prog.scalars
+    rop, acc_dt, res_dt, post = reduce
+    A = ctype(acc_dt)
+    n_ops = max(len(arrays), 1)
+    src = []
+    w = src.append
+    w(f"struct Geo_{name} {{ i64 outer; i64 red; i64 inner; i64 so[{n_ops}]; i64 sr[{n_ops}]; i64 si[{n_ops}]; }};")
+    params = [f"const Geo_{name} g"]
+    for i, a in enumerate(arrays):
+        params.append(f"const char* __restrict__ in{i}")
+    for j, (_, dt) in enumerate(scalars):
+        params.append(f"const {ctype(dt)} s{j}")
+    params += [f"{ctype(res_dt)}* __restrict__ result", "const double post_scale"]
+    body = emit_body(prog)
+    w(f'extern "C" __global__ void __launch_bounds__({threads}) {name}({", ".join(params)}) {{')
+    for i, (a, c) in enumerate(zip(arrays, in_class)):
+        if c == "b":
+            w(f"  const {ctype(a.dtype)} x{i} = *reinterpret_cast<const {ctype(a.dtype)}*>(in{i});")
+    w("  const i64 total = g.outer * g.inner;")
+    w("  for (i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (i64)gridDim.x * blockDim.x) {")
+    w("    const i64 o = idx / g.inner, c = idx - o * g.inner;")
+    w(f"    {A} acc = {_identity(rop, acc_dt)};")
+    w("    for (i64 r = 0; r < g.red; ++r) {")
+    for i, (a, c) in enumerate(zip(arrays, in_class)):
+        if c != "b":
+            w(f"      const {ctype(a.dtype)} x{i} = *reinterpret_cast<const {ctype(a.dtype)}*>"
+              f"(in{i} + o * g.so[{i}] + r * g.sr[{i}] + c * g.si[{i}]);")
+    for line in body:
+        w(f"      {line}")
+    w(f"      acc = {_RED[rop]}::op(acc, ({A}){_operand_name(prog.roots[0])});")
+    w("    }")
+    fin = f"({ctype(res_dt)})(acc / ({A})post_scale)" if np.dtype(acc_dt).kind == "f" \
+        else f"({ctype(res_dt)})acc"
+    w(f"    result[idx] = {fin};")
+    w("  }")
+    w("}")
+    return "\n".join(src) + "\n"

@@ -1,0 +1,1028 @@
+"""Capture layer: the drop-in NumPy surface of DelayRepay, rebuilt for the B200 engine.
+
+Mirrors the reference's operator/plugin interface for the hot path (same class and function
+names, argument meaning and error behaviour) -- reference file:line in brackets:
+
+  DelayArray            [delayarray.py:25-157]   NDArrayOperatorsMixin capture object
+  Memoiser / reset      [delayarray.py:216-236]  hash-consing (np.sin(a) is np.sin(a))
+  NumpyEx, BinaryNumpyEx, UnaryFuncEx, BinaryFuncEx, Scalar, NPArray, ReduceEx, MMEx, MVEx,
+  DotEx                 [delayarray.py:239-452]  graph IR (ReduceEx/MMEx/MVEx/DotEx are dead
+                                                  stubs in the reference; real lazy nodes here)
+  create_ex, pow_ex, arg_to_numpy_ex             [delayarray.py:316-336,470-479]
+  HANDLED_FUNCTIONS / implements                 [delayarray.py:482-568,608-615]
+  creation functions + aliases                   [delayarray.py:571-606,618-644]
+
+What changed relative to the reference (documented divergences):
+NumPy-exact dtype promotion (ufunc.resolve_dtypes, NEP 50 weak scalars) and broadcasting stay
+lazy instead of dropping to eager library calls; reductions/dot/matmul are lazy nodes that fuse
+their elementwise producer; views of leaves are zero-copy and hash-consed by layout; memoised
+results are invalidated by buffer version counters; the memo table holds weak references.
+Evaluation is forced by get()/__array__/print/indexing exactly as in the reference.
+"""
+import weakref
+from numbers import Number
+
+import numpy as np
+import numpy.lib.mixins
+
+from . import backend as _be
+from .device import DeviceArray
+
+_backend = _be.backend
+
+
+def cast(func):
+    """Wrap a backend constructor so it returns a graph leaf  [delayarray.py:13-22]."""
+
+    def wrapper(*args, **kwargs):
+        arr = func(*args, **kwargs)
+        if not isinstance(arr, DelayArray):
+            arr = NPArray(arr)
+        return arr
+
+    wrapper.__name__ = getattr(func, "__name__", "wrapped")
+    return wrapper
+
+
+# --------------------------------------------------------------------------- op tables
+# ufunc name -> C spelling for the four "operator" nodes  [delayarray.py:162-168]
+OPS = {"add": "+", "multiply": "*", "subtract": "-", "true_divide": "/", "divide": "/"}
+
+# every other elementwise ufunc the code generator knows  [delayarray.py:171-186, extended]
+FUNCS = {
+    "power": "pow", "arctan2": "atan2", "absolute": "abs", "fabs": "abs", "sin": "sin",
+    "cos": "cos", "tan": "tan", "sqrt": "sqrt", "log": "log", "negative": "-", "exp": "exp",
+    "tanh": "tanh", "sinh": "sinh", "cosh": "cosh",
+    # beyond the reference's table (KeyError there)
+    "positive": "+", "exp2": "exp2", "expm1": "expm1", "log2": "log2", "log10": "log10",
+    "log1p": "log1p", "arcsin": "asin", "arccos": "acos", "arctan": "atan",
+    "arcsinh": "asinh", "arccosh": "acosh", "arctanh": "atanh", "cbrt": "cbrt",
+    "reciprocal": "rcp", "floor": "floor", "ceil": "ceil", "trunc": "trunc", "rint": "rint",
+    "sign": "sign", "hypot": "hypot", "copysign": "copysign", "maximum": "max",
+    "minimum": "min", "fmax": "fmax", "fmin": "fmin", "fmod": "fmod",
+    "remainder": "remainder", "floor_divide": "floor_divide", "erf": "erf", "erfc": "erfc",
+    "greater": ">", "greater_equal": ">=", "less": "<", "less_equal": "<=", "equal": "==",
+    "not_equal": "!=", "logical_and": "&&", "logical_or": "||", "logical_not": "!",
+    "logical_xor": "^^", "bitwise_and": "&", "bitwise_or": "|", "bitwise_xor": "^",
+    "invert": "~", "left_shift": "<<", "right_shift": ">>", "isnan": "isnan",
+    "isinf": "isinf", "isfinite": "isfinite", "signbit": "signbit", "deg2rad": "deg2rad",
+    "rad2deg": "rad2deg", "radians": "deg2rad", "degrees": "rad2deg",
+}
+
+_REDUCE_UFUNCS = {"add": "sum", "multiply": "prod", "maximum": "max", "minimum": "min"}
+
+
+# --------------------------------------------------------------------------- hash-consing
+class Memoiser(type):
+    """Metaclass: structurally equal constructor calls return the same node while it is alive
+    [delayarray.py:216-231].  Unlike the reference the table holds weak references (no leak)
+    and keys carry the class and the scalar's *type* (no 2 / 2.0 / True collisions)."""
+
+    _cache = weakref.WeakValueDictionary()
+
+    def __call__(cls, *args, **kwargs):
+        key = cls._memo_key(*args, **kwargs)
+        if key is None:
+            return super().__call__(*args, **kwargs)
+        hit = Memoiser._cache.get(key)
+        if hit is None:
+            hit = super().__call__(*args, **kwargs)
+            Memoiser._cache[key] = hit
+        return hit
+
+
+def reset():
+    """Forget every memoised node  [delayarray.py:234-236]."""
+    Memoiser._cache.clear()
+
+
+def _layout_of(arr):
+    """(buffer identity, byte offset, shape, strides, dtype) of a host or device array."""
+    if isinstance(arr, DeviceArray):
+        return arr.layout_key()
+    base = arr
+    while isinstance(base.base, np.ndarray):
+        base = base.base
+    off = arr.__array_interface__["data"][0] - base.__array_interface__["data"][0]
+    return (id(base), off, arr.shape, arr.strides, arr.dtype.str)
+
+
+# --------------------------------------------------------------------------- DelayArray
+class DelayArray(numpy.lib.mixins.NDArrayOperatorsMixin):
+    """Lazy array: NumPy calls on it build graph nodes; see module docstring."""
+
+    count = 0
+    __array_priority__ = 100.0
+    kind = "node"
+
+    def __init__(self, *args, **kwargs):
+        self._count = DelayArray.count
+        DelayArray.count += 1
+        self._stamp = None
+
+    # ---- forcing points  [delayarray.py:35-44,101-112]
+    def _force(self):
+        """Evaluate (once) and return the backend array; re-evaluates when a buffer this
+        result was computed from has been written since (buffer version counters)."""
+        arr = self.__dict__.get("array")
+        if arr is not None and _stamp_valid(self._stamp):
+            return arr
+        self.array = _backend.run(self)
+        return self.array
+
+    def __array__(self, dtype=None, copy=None):
+        host = self.get()
+        return host if dtype is None else host.astype(dtype, copy=False)
+
+    def get(self, out=None):
+        """Evaluate and copy to the host; returns a numpy.ndarray."""
+        arr = self._force()
+        return arr.get(out=out) if out is not None else arr.get()
+
+    def run(self):
+        self._force()
+        return self
+
+    def __repr__(self):
+        return str(self.get())
+
+    def __bool__(self):
+        if self.size == 1:
+            return bool(self.get())
+        return self.shape[0] != 0          # reference: truthiness falls through to __len__
+
+    def __float__(self):
+        return float(self.get())
+
+    def __int__(self):
+        return int(self.get())
+
+    def __len__(self):
+        return self.shape[0]
+
+    def item(self):
+        return self.get().item()
+
+    # ---- capture  [delayarray.py:46-61]
+    def __array_ufunc__(self, ufunc, method, *inputs, **kwargs):
+        out = kwargs.pop("out", None)
+        if out is not None or kwargs.pop("where", True) is not True:
+            return NotImplemented
+        dtype = kwargs.pop("dtype", None)
+        name = ufunc.__name__
+        if method == "reduce":
+            if name not in _REDUCE_UFUNCS:
+                raise KeyError(name)
+            res = ReduceEx(ufunc, arg_to_numpy_ex(inputs[0]), _norm_axis(kwargs.get("axis", 0)),
+                           bool(kwargs.get("keepdims", False)))
+            return res if dtype is None else res.astype(dtype)
+        if method != "__call__":
+            return NotImplemented
+        if name == "matmul":
+            return self._dot(inputs, kwargs)
+        args = [arg_to_numpy_ex(arg) for arg in inputs]
+        res = create_ex(ufunc, args)
+        return res if dtype is None else res.astype(dtype)
+
+    def __array_function__(self, func, types, args, kwargs):        # [delayarray.py:87-90]
+        if func.__name__ == "dot":
+            return self._dot(args, kwargs)
+        return HANDLED_FUNCTIONS[func](*args, **kwargs)             # KeyError: unsupported
+
+    # ---- contractions  [delayarray.py:63-85,98-99]
+    def _dot(self, args, kwargs=None):
+        left, right = (arg_to_numpy_ex(a) for a in list(args)[:2])
+        if left.ndim == 0 or right.ndim == 0:
+            return create_ex(np.multiply, [left, right])
+        if left.ndim == 1 and right.ndim == 1:
+            return DotEx(left, right)
+        if left.ndim == 2 and right.ndim == 1:
+            return MVEx(left, right)
+        if left.ndim == 2 and right.ndim == 2:
+            return MMEx(left, right)
+        if left.ndim == 1 and right.ndim == 2:
+            return MVEx(transpose(right), left)
+        raise NotImplementedError(f"dot of shapes {left.shape} and {right.shape}")
+
+    def __matmul__(self, other):
+        return self._dot([self, other])
+
+    def __rmatmul__(self, other):
+        return self._dot([other, self])
+
+    def dot(self, other, out=None):
+        # the reference passes `other` as the argument list and returns b[0].b[1]
+        # (delayarray.py:98-99); NumPy semantics are implemented instead.
+        return self._dot([self, other])
+
+    # ---- views and assignment  [delayarray.py:111-128]
+    def reshape(self, *args, **kwargs):
+        return NPArray(self._force().reshape(*args, **kwargs))
+
+    def __getitem__(self, key):
+        if isinstance(key, DelayArray):
+            raise NotImplementedError("boolean / integer-array indexing is not supported yet")
+        return NPArray(self._force()[key])
+
+    def __setitem__(self, key, item):
+        if isinstance(key, DelayArray):
+            raise NotImplementedError("boolean / integer-array assignment is not supported yet")
+        self._force()[key] = item
+
+    # ---- conveniences of the reference object  [delayarray.py:130-146]
+    def astype(self, dtype, copy=True):
+        dtype = np.dtype(dtype)
+        if dtype == self.dtype:
+            return self
+        return CastEx(self, dtype)
+
+    def sum(self, *args, **kwargs):
+        return np.sum(self, *args, **kwargs)
+
+    def mean(self, *args, **kwargs):
+        return np.mean(self, *args, **kwargs)
+
+    def max(self, *args, **kwargs):
+        return np.max(self, *args, **kwargs)
+
+    def min(self, *args, **kwargs):
+        return np.min(self, *args, **kwargs)
+
+    def prod(self, *args, **kwargs):
+        return np.prod(self, *args, **kwargs)
+
+    def var(self, *args, **kwargs):
+        return np.var(self, *args, **kwargs)
+
+    def std(self, *args, **kwargs):
+        return np.std(self, *args, **kwargs)
+
+    def repeat(self, *args, **kwargs):
+        return np.repeat(self, *args, **kwargs)
+
+    def transpose(self, *axes):
+        return np.transpose(self, axes if axes else None)
+
+    def copy(self):
+        return NPArray(self._force().copy())
+
+    @property
+    def T(self):
+        if len(self.shape) == 1:
+            return self
+        return np.transpose(self)
+
+    @property
+    def ndim(self):
+        return len(self.shape)
+
+    @property
+    def size(self):
+        n = 1
+        for s in self.shape:
+            n *= s
+        return n
+
+    # ---- code-generation names  [delayarray.py:150-156]
+    @property
+    def name(self):
+        return f"arr{self._count}"
+
+    @property
+    def inputs(self):
+        """name -> leaf for every array leaf below this node (DAG walk, each node once)."""
+        found, seen, stack = {}, set(), [self]
+        while stack:
+            node = stack.pop()
+            if id(node) in seen:
+                continue
+            seen.add(id(node))
+            if isinstance(node, NPArray):
+                found[node.name] = node
+            stack.extend(getattr(node, "children", ()))
+        return dict(sorted(found.items(), key=lambda kv: kv[1]._count))
+
+
+def _stamp_valid(stamp):
+    if stamp is None:
+        return True
+    for buf_ref, version in stamp:
+        buf = buf_ref()
+        if buf is None or buf.version != version:
+            return False
+    return True
+
+
+def _norm_axis(axis):
+    if axis is None or isinstance(axis, tuple):
+        return axis
+    return int(axis)
+
+
+Shape = tuple
+
+
+class NumpyEx(DelayArray, metaclass=Memoiser):
+    """Graph node base  [delayarray.py:239-264]."""
+
+    children = ()
+
+    @classmethod
+    def _memo_key(cls, *args, **kwargs):
+        return None
+
+    def __hash__(self):
+        return id(self)
+
+    def __eq__(self, other):          # keep NumPy semantics for `==` (the mixin's ufunc path)
+        return np.equal(self, other)
+
+    def __ne__(self, other):
+        return np.not_equal(self, other)
+
+
+class Funcable:
+    def to_op(self):
+        return OPS.get(self.func.__name__) or FUNCS[self.func.__name__]
+
+
+def _kid_key(node):
+    return id(node)
+
+
+_RESOLVE_CACHE = {}
+
+
+def resolve_loop(ufunc, kids):
+    """NumPy's own type resolution: (input loop dtypes, output dtype), NEP 50 weak scalars."""
+    sig = tuple(k.weak_type if (isinstance(k, Scalar) and k.weak_type is not None) else k.dtype
+                for k in kids)
+    key = (ufunc, sig)
+    hit = _RESOLVE_CACHE.get(key)
+    if hit is None:
+        try:
+            res = ufunc.resolve_dtypes(sig + (None,) * ufunc.nout)
+        except TypeError:
+            # all-weak inputs: resolve on concrete default dtypes instead
+            res = ufunc.resolve_dtypes(tuple(np.result_type(s) for s in sig) + (None,) * ufunc.nout)
+        hit = (tuple(res[:ufunc.nin]), res[ufunc.nin])
+        for dt in hit[0] + (hit[1],):
+            if dt.kind not in "biuf":
+                raise TypeError(f"{ufunc.__name__}: dtype {dt} is not supported on the device")
+        _RESOLVE_CACHE[key] = hit
+    return hit
+
+
+class _Elementwise(NumpyEx, Funcable):
+    """Shared body of the three elementwise node classes."""
+
+    kind = "ewise"
+
+    def __init__(self, func, *kids):
+        super().__init__()
+        if func.__name__ not in OPS and func.__name__ not in FUNCS:
+            raise KeyError(func.__name__)          # reference error behaviour: KeyError
+        self.func = func
+        self.op = func.__name__
+        self.children = list(kids)
+        self.loop, self.dtype = resolve_loop(func, kids)
+        self.shape = np.broadcast_shapes(*[k.shape for k in kids])
+
+    @classmethod
+    def _memo_key(cls, func, *kids):
+        return (cls.__name__, func.__name__) + tuple(_kid_key(k) for k in kids)
+
+
+class BinaryNumpyEx(_Elementwise):
+    """a (+ - * /) b  [delayarray.py:339-351]."""
+
+    @property
+    def name(self):
+        return f"binex{self._count}"
+
+
+class UnaryFuncEx(_Elementwise):
+    """f(a)  [delayarray.py:286-298]."""
+
+    @property
+    def name(self):
+        return f"unfunc{self._count}"
+
+
+class BinaryFuncEx(_Elementwise):
+    """f(a, b)  [delayarray.py:301-313]."""
+
+    @property
+    def name(self):
+        return f"binfun{self._count}"
+
+
+class WhereEx(NumpyEx):
+    """np.where(cond, a, b) as a lazy ternary node (new; the reference has no handler)."""
+
+    kind = "ewise"
+    op = "where"
+
+    def __init__(self, cond, a, b):
+        super().__init__()
+        self.func = np.where
+        self.children = [cond, a, b]
+        sig = [k.weak_type if (isinstance(k, Scalar) and k.weak_type is not None) else k.dtype
+               for k in (a, b)]
+        out = np.result_type(*sig)
+        self.loop, self.dtype = (np.dtype(bool), out, out), out
+        self.shape = np.broadcast_shapes(cond.shape, a.shape, b.shape)
+
+    @classmethod
+    def _memo_key(cls, *kids):
+        return (cls.__name__,) + tuple(_kid_key(k) for k in kids)
+
+    @property
+    def name(self):
+        return f"where{self._count}"
+
+
+class CastEx(NumpyEx):
+    """astype on a lazy node (the reference only has the in-place leaf astype, :401-408)."""
+
+    kind = "ewise"
+    op = "cast"
+
+    def __init__(self, arg, dtype):
+        super().__init__()
+        self.func = None
+        self.children = [arg]
+        self.dtype = np.dtype(dtype)
+        src = arg.dtype if arg.dtype is not None else np.result_type(arg.weak_type)
+        self.loop = (src,)
+        self.shape = arg.shape
+
+    @classmethod
+    def _memo_key(cls, arg, dtype):
+        return (cls.__name__, _kid_key(arg), np.dtype(dtype).str)
+
+    @property
+    def name(self):
+        return f"cast{self._count}"
+
+
+class ReduceEx(NumpyEx, Funcable):
+    """func.reduce(arg, axis)  [delayarray.py:272-283]; fused with its elementwise producer.
+    ``post`` = "mean" divides by the reduced count in the kernel epilogue."""
+
+    kind = "reduce"
+
+    def __init__(self, func, arg, axis=None, keepdims=False, post=None):
+        super().__init__()
+        self.func = func
+        self.op = _REDUCE_UFUNCS[func.__name__]
+        self.children = [arg]
+        self.post = post
+        nd = arg.ndim
+        if axis is None:
+            axes = tuple(range(nd))
+        else:
+            axes = tuple(sorted({(a + nd) % nd if nd else 0 for a in
+                                 (axis if isinstance(axis, tuple) else (axis,))}))
+            if nd == 0:
+                axes = ()
+        self.axes = axes
+        self.keepdims = keepdims
+        self.shape = tuple((1 if i in axes else s) for i, s in enumerate(arg.shape)
+                           if keepdims or i not in axes)
+        src = arg.dtype
+        if self.op in ("sum", "prod"):
+            # NumPy promotes small integers / bool to the platform integer for add.reduce
+            if src.kind == "b" or (src.kind == "i" and src.itemsize < 8):
+                src = np.dtype(np.int64)
+            elif src.kind == "u" and src.itemsize < 8:
+                src = np.dtype(np.uint64)
+        if post == "mean" and src.kind in "biu":
+            src = np.dtype(np.float64)
+        self.dtype = src
+
+    @classmethod
+    def _memo_key(cls, func, arg, axis=None, keepdims=False, post=None):
+        return (cls.__name__, func.__name__, _kid_key(arg), axis, keepdims, post)
+
+    @property
+    def name(self):
+        return f"redex{self._count}"
+
+
+class _Contraction(NumpyEx, Funcable):
+    kind = "matmul"
+
+    def __init__(self, arg1, arg2):
+        super().__init__()
+        self.func = np.dot
+        self.arg1, self.arg2 = arg1, arg2
+        self.children = [arg1, arg2]
+        self.dtype = np.result_type(arg1.dtype, arg2.dtype)
+        if self.dtype.kind not in "f":
+            self.dtype = np.result_type(self.dtype)      # integer dot keeps the integer type
+        self._inshape = arg1.shape
+
+    @classmethod
+    def _memo_key(cls, a, b):
+        return (cls.__name__, _kid_key(a), _kid_key(b))
+
+
+class DotEx(_Contraction):
+    """1-d . 1-d -> scalar  [delayarray.py:374-380]; runs as a fused multiply + full reduce."""
+
+    def __init__(self, left, right):
+        if left.shape != right.shape:
+            raise ValueError(f"shapes {left.shape} and {right.shape} not aligned")
+        super().__init__(left, right)
+        self.shape = ()
+
+    @property
+    def name(self):
+        return f"dotex{self._count}"
+
+
+class MVEx(_Contraction):
+    """matrix @ vector  [delayarray.py:364-371]; a fused row reduction (HBM-bound)."""
+
+    def __init__(self, mat, vec):
+        if mat.shape[1] != vec.shape[0]:
+            raise ValueError(f"shapes {mat.shape} and {vec.shape} not aligned")
+        super().__init__(mat, vec)
+        self.shape = (mat.shape[0],)
+
+    @property
+    def name(self):
+        return f"mvex{self._count}"
+
+
+class MMEx(_Contraction):
+    """matrix @ matrix  [delayarray.py:354-361]."""
+
+    def __init__(self, a, b):
+        if a.shape[1] != b.shape[0]:
+            raise ValueError(f"shapes {a.shape} and {b.shape} not aligned")
+        super().__init__(a, b)
+        self.shape = (a.shape[0], b.shape[1])
+
+    @property
+    def name(self):
+        return f"mmex{self._count}"
+
+
+class NPArray(NumpyEx):
+    """Graph leaf wrapping a backend (device) array  [delayarray.py:383-417].  A host
+    numpy.ndarray is accepted too: it is uploaded once, on first evaluation."""
+
+    kind = "leaf"
+
+    def __init__(self, array):
+        super().__init__()
+        if not isinstance(array, (DeviceArray, np.ndarray)):
+            array = np.asarray(array)
+        if array.dtype.kind not in "biuf":
+            raise TypeError(f"dtype {array.dtype} is not supported on the device")
+        self.array = array
+        self.shape = tuple(array.shape)
+        self.dtype = array.dtype
+
+    @classmethod
+    def _memo_key(cls, array):
+        if isinstance(array, DeviceArray):
+            return ("NPArray",) + array.layout_key()      # the same slice twice is one leaf
+        if isinstance(array, np.ndarray):
+            return ("NPArray", id(array))                  # reference: id(array), :225-226
+        return None
+
+    def _force(self):
+        arr = self.array
+        if not isinstance(arr, DeviceArray):
+            dev = self.__dict__.get("_dev")
+            if dev is None:
+                dev = self._dev = DeviceArray.from_host(arr)
+            return dev
+        return arr
+
+    def __hash__(self):
+        return id(self)
+
+    def astype(self, *args, **kwargs):
+        """In place, like the reference's leaf astype  [delayarray.py:401-408]."""
+        dtype = np.dtype(args[0] if args else kwargs["dtype"])
+        if dtype == self.dtype:
+            return self
+        old_key = self._memo_key(self.array)
+        self.array = self.array.astype(dtype)
+        self.__dict__.pop("_dev", None)
+        self.dtype = self.array.dtype
+        if Memoiser._cache.get(old_key) is self:
+            del Memoiser._cache[old_key]
+        Memoiser._cache[self._memo_key(self.array)] = self
+        return self
+
+    @property
+    def name(self):
+        return f"arr{self._count}"
+
+
+class NPRef(NumpyEx):
+    """Reference to an already evaluated node  [delayarray.py:420-431]; the planner uses it
+    when it cuts a region at a materialised producer."""
+
+    kind = "leaf"
+
+    def __init__(self, node, shape=None):
+        super().__init__()
+        self.ref = node
+        self.shape = tuple(node.shape if shape is None else shape)
+        self.dtype = node.dtype
+
+    @property
+    def array(self):
+        return self.ref._force()
+
+    def _force(self):
+        return self.ref._force()
+
+
+class Scalar(NumpyEx):
+    """A scalar operand  [delayarray.py:434-452].  Python numbers stay *weak* (NEP 50): they
+    take the dtype of the array they meet and reach the kernel as a typed argument, never as
+    a literal in the source (so kernels are shared across scalar values)."""
+
+    kind = "scalar"
+
+    def __init__(self, val):
+        super().__init__()
+        self.val = val
+        self.shape = ()
+        if isinstance(val, (bool, np.bool_)):
+            self.weak_type, self.dtype = None, np.dtype(bool)
+        elif isinstance(val, np.generic):
+            self.weak_type, self.dtype = None, val.dtype
+        elif isinstance(val, int):
+            self.weak_type, self.dtype = int, None
+        elif isinstance(val, float):
+            self.weak_type, self.dtype = float, None
+        else:
+            raise TypeError(f"unsupported scalar {type(val)}")
+
+    @classmethod
+    def _memo_key(cls, val):
+        if val != val:
+            return None
+        return ("Scalar", type(val).__name__, val)
+
+    def __hash__(self):
+        return id(self)
+
+    def _force(self):
+        raise TypeError("a Scalar has no array")
+
+    @property
+    def name(self):
+        return str(self.val)
+
+    @property
+    def inputs(self):
+        return {}
+
+
+def is_matrix_matrix(left, right):
+    return len(left) > 1 and len(right) > 1
+
+
+def is_matrix_vector(left, right):
+    return len(left) > 1 and len(right) == 1
+
+
+# --------------------------------------------------------------------------- node builders
+def arg_to_numpy_ex(arg):
+    """[delayarray.py:470-479]"""
+    if isinstance(arg, DelayArray):
+        return arg
+    if isinstance(arg, Number):
+        return Scalar(arg)
+    if _backend.is_ndarray(arg) or isinstance(arg, np.ndarray):
+        return NPArray(arg)
+    if isinstance(arg, (list, tuple)):
+        return NPArray(np.asarray(arg))
+    print(type(arg))
+    raise NotImplementedError
+
+
+def pow_ex(func, left, right):
+    """x ** k for a Python-int k >= 2 becomes the left-associated chain ((x*x)*x)...
+    [delayarray.py:316-324] -- the reference's CPU path evaluates exactly that, and it rounds
+    differently from np.power in ~27 % of samples, so the association order is kept.
+    k in {1, 0, negative}: NumPy semantics (the reference returns x itself -- a defect)."""
+    if not (isinstance(right, Scalar) and right.weak_type is int):
+        return BinaryFuncEx(func, left, right)
+    k = right.val
+    if k >= 2:
+        ex = left
+        for _ in range(k - 1):
+            ex = BinaryNumpyEx(np.multiply, ex, left)
+        return ex
+    if k < 0 and left.dtype.kind in "iub":
+        raise ValueError("Integers to negative integer powers are not allowed.")
+    return BinaryFuncEx(func, left, right)
+
+
+def create_ex(func, args):
+    """[delayarray.py:327-336]"""
+    name = func.__name__
+    if name in OPS:
+        return BinaryNumpyEx(func, *args)
+    if name == "square":
+        return BinaryNumpyEx(np.multiply, args[0], args[0])
+    if len(args) == 1:
+        return UnaryFuncEx(func, *args)
+    if name == "power":
+        return pow_ex(func, *args)
+    return BinaryFuncEx(func, *args)
+
+
+# --------------------------------------------------------------------------- __array_function__
+HANDLED_FUNCTIONS = {}
+
+
+def implements(np_function):
+    "Register an __array_function__ implementation  [delayarray.py:485-490]."
+
+    def decorator(func):
+        HANDLED_FUNCTIONS[np_function] = func
+        return func
+
+    return decorator
+
+
+def _reduce(ufunc, arr, axis=None, dtype=None, out=None, keepdims=False, post=None, **kw):
+    if out is not None:
+        raise NotImplementedError("out= is not supported")
+    node = arg_to_numpy_ex(arr)
+    if dtype is not None:
+        node = node.astype(dtype)
+    if keepdims is np._NoValue:
+        keepdims = False
+    return ReduceEx(ufunc, node, _norm_axis(axis), bool(keepdims), post)
+
+
+@implements(np.sum)
+def sum(arr, *args, **kwargs):                      # noqa: A001  [delayarray.py:516-518]
+    return _reduce(np.add, arr, *args, **kwargs)
+
+
+@implements(np.prod)
+def prod(arr, *args, **kwargs):
+    return _reduce(np.multiply, arr, *args, **kwargs)
+
+
+@implements(np.max)
+def max(arr, *args, **kwargs):                      # noqa: A001  [delayarray.py:533-535]
+    return _reduce(np.maximum, arr, *args, **kwargs)
+
+
+@implements(np.min)
+def min(arr, *args, **kwargs):                      # noqa: A001
+    return _reduce(np.minimum, arr, *args, **kwargs)
+
+
+@implements(np.mean)
+def mean(arr, *args, **kwargs):
+    return _reduce(np.add, arr, *args, post="mean", **kwargs)
+
+
+@implements(np.average)
+def average(arr, axis=None, weights=None, **kwargs):            # [delayarray.py:544-546]
+    if weights is None:
+        return mean(arr, axis=axis, **kwargs)
+    w = arg_to_numpy_ex(weights)
+    return np.sum(arg_to_numpy_ex(arr) * w, axis=axis) / np.sum(w, axis=axis)
+
+
+@implements(np.var)
+def var(arr, axis=None, dtype=None, out=None, ddof=0, keepdims=False, **kw):   # [:511-513]
+    x = arg_to_numpy_ex(arr)
+    if dtype is not None:
+        x = x.astype(dtype)
+    mu = mean(x, axis=axis, keepdims=True).run()
+    dev = x - mu
+    ss = np.sum(dev * dev, axis=axis, keepdims=bool(keepdims))
+    n = x.size if axis is None else int(np.prod([x.shape[a] for a in np.atleast_1d(axis)]))
+    return ss / float(n - ddof)
+
+
+@implements(np.std)
+def std(arr, *args, **kwargs):
+    return np.sqrt(var(arr, *args, **kwargs))
+
+
+@implements(np.linalg.norm)
+def norm(x, ord=None, axis=None, keepdims=False):
+    if ord not in (None, 2, "fro") or (ord == 2 and arg_to_numpy_ex(x).ndim > 1 and axis is None):
+        raise NotImplementedError("only the 2-norm / Frobenius norm is supported")
+    x = arg_to_numpy_ex(x)
+    return np.sqrt(np.sum(x * x, axis=axis, keepdims=keepdims))
+
+
+@implements(np.where)
+def where(cond, a=None, b=None):
+    if a is None or b is None:
+        raise NotImplementedError("single-argument np.where is not supported")
+    return WhereEx(arg_to_numpy_ex(cond), arg_to_numpy_ex(a), arg_to_numpy_ex(b))
+
+
+@implements(np.clip)
+def clip(a, a_min=None, a_max=None, **kw):
+    res = arg_to_numpy_ex(a)
+    if a_min is not None:
+        res = np.maximum(res, a_min)
+    if a_max is not None:
+        res = np.minimum(res, a_max)
+    return res
+
+
+@implements(np.transpose)
+def transpose(arr, axes=None):                                   # [delayarray.py:521-524]
+    dev = arg_to_numpy_ex(arr)._force()
+    return NPArray(dev.transpose(axes) if axes is not None else dev.T)
+
+
+@implements(np.matmul)
+def matmul(a, b, **kw):
+    return arg_to_numpy_ex(a)._dot([a, b]) if isinstance(a, DelayArray) else b._dot([a, b])
+
+
+@implements(np.roll)
+def roll(arr, shift, axis=None):                                 # [delayarray.py:527-530]
+    src = arg_to_numpy_ex(arr)._force()
+    flat = src.reshape(-1) if axis is None else src
+    ax = 0 if axis is None else axis % flat.ndim
+    n = flat.shape[ax]
+    out = DeviceArray.empty(flat.shape, flat.dtype, flat.dev)
+    k = shift % n if n else 0
+
+    def sl(a, b):
+        return tuple(slice(a, b) if i == ax else slice(None) for i in range(flat.ndim))
+    if k:
+        out[sl(k, None)] = flat[sl(None, n - k)]
+        out[sl(None, k)] = flat[sl(n - k, None)]
+    else:
+        out[...] = flat
+    return NPArray(out.reshape(src.shape) if axis is None else out)
+
+
+@implements(np.repeat)
+def repeat(arr, repeats, axis=None):                             # [delayarray.py:549-552]
+    src = arg_to_numpy_ex(arr)._force()
+    if not isinstance(repeats, (int, np.integer)):
+        raise NotImplementedError("per-element repeat counts are not supported")
+    if axis is None:
+        src, axis = src.reshape(-1), 0
+    axis %= src.ndim
+    shp = src.shape[:axis + 1] + (int(repeats),) + src.shape[axis + 1:]
+    st = src.strides[:axis + 1] + (0,) + src.strides[axis + 1:]
+    wide = DeviceArray(src.buf, shp, src.dtype, st, src.offset).copy()
+    return NPArray(wide.reshape(src.shape[:axis] + (src.shape[axis] * int(repeats),)
+                                + src.shape[axis + 1:]))
+
+
+@implements(np.tile)
+def tile(arr, reps):                                             # [delayarray.py:608-615]
+    src = arg_to_numpy_ex(arr)._force()
+    reps = (reps,) if isinstance(reps, (int, np.integer)) else tuple(reps)
+    nd = builtins_max(len(reps), src.ndim)
+    reps = (1,) * (nd - len(reps)) + reps
+    shape = (1,) * (nd - src.ndim) + src.shape
+    strides = (0,) * (nd - src.ndim) + src.strides
+    shp, st, final = [], [], []
+    for r, n, s in zip(reps, shape, strides):
+        shp += [int(r), n]
+        st += [0, s]
+        final.append(int(r) * n)
+    wide = DeviceArray(src.buf, shp, src.dtype, st, src.offset).copy()
+    return NPArray(wide.reshape(tuple(final)))
+
+
+@implements(np.diag)
+def diag(arr, k=0):                                              # [delayarray.py:493-501]
+    src = arg_to_numpy_ex(arr)._force()
+    if src.ndim == 1:
+        return diagflat(arr, k)
+    rows, cols = src.shape
+    r0, c0 = (0, k) if k >= 0 else (-k, 0)
+    n = builtins_max(0, builtins_min(rows - r0, cols - c0))
+    view = DeviceArray(src.buf, (n,), src.dtype, (src.strides[0] + src.strides[1],),
+                       src.offset + r0 * src.strides[0] + c0 * src.strides[1])
+    return NPArray(view)
+
+
+@implements(np.diagflat)
+def diagflat(arr, k=0):                                          # [delayarray.py:504-508]
+    src = arg_to_numpy_ex(arr)._force().reshape(-1)
+    n = src.shape[0] + abs(k)
+    out = DeviceArray.empty((n, n), src.dtype, src.dev)
+    out[...] = 0
+    r0, c0 = (0, k) if k >= 0 else (-k, 0)
+    item = src.dtype.itemsize
+    view = DeviceArray(out.buf, (src.shape[0],), src.dtype, ((n + 1) * item,),
+                       (r0 * n + c0) * item)
+    view[...] = src
+    return NPArray(out)
+
+
+@implements(np.cumsum)
+def cumsum(arr, axis=None, dtype=None, out=None):                # [delayarray.py:555-558]
+    from . import engine
+    node = arg_to_numpy_ex(arr)
+    if dtype is not None:
+        node = node.astype(dtype)
+    return NPArray(engine.cumsum(node._force(), axis))
+
+
+import builtins as _builtins          # noqa: E402
+builtins_max, builtins_min = _builtins.max, _builtins.min
+
+
+def greater(arr1, arr2, *args, **kwargs):                        # [delayarray.py:561-563]
+    return np.greater(arr1, arr2, *args, **kwargs)
+
+
+def less(arr1, arr2, *args, **kwargs):                           # [delayarray.py:566-568]
+    return np.less(arr1, arr2, *args, **kwargs)
+
+
+def evaluate(*arrays):
+    """Co-evaluate several lazy arrays in as few fused kernels as possible (one kernel when
+    they share an iteration space, e.g. Black-Scholes call and put: 20 B/option instead of
+    32).  SURVEY.md section 8f rank 4; the reference has no equivalent."""
+    nodes = [a for a in arrays if isinstance(a, DelayArray)]
+    _backend.run_many(nodes)
+    return arrays
+
+
+# --------------------------------------------------------------------------- aliases
+add = np.add                                                     # [delayarray.py:571-587]
+multiply = np.multiply
+dot = np.dot
+cos = np.cos
+sin = np.sin
+tan = np.tan
+tanh = np.tanh
+sinh = np.sinh
+cosh = np.cosh
+arctan2 = np.arctan2
+subtract = np.subtract
+exp = np.exp
+log = np.log
+power = np.power
+sqrt = np.sqrt
+square = np.square
+abs = np.abs                                                     # noqa: A001
+maximum = np.maximum
+minimum = np.minimum
+divide = np.divide
+true_divide = np.true_divide
+negative = np.negative
+newaxis = _backend.fallback.newaxis
+
+double = np.double                                               # [delayarray.py:590-593]
+float64 = np.float64
+float32 = np.float32
+int32 = np.int32
+int64 = np.int64
+uint32 = np.uint32
+bool_ = np.bool_
+
+empty = cast(_backend.fallback.empty)                            # [delayarray.py:596-605]
+empty_like = cast(_backend.fallback.empty_like)
+eye = cast(_backend.fallback.eye)
+identity = cast(_backend.fallback.identity)
+ones = cast(_backend.fallback.ones)
+ones_like = cast(_backend.fallback.ones_like)
+zeros = cast(_backend.fallback.zeros)
+zeros_like = cast(_backend.fallback.zeros_like)
+full = cast(_backend.fallback.full)
+full_like = cast(_backend.fallback.full_like)
+
+array = cast(_backend.fallback.array)                            # [delayarray.py:620-631]
+asarray = cast(_backend.fallback.asarray)
+asanyarray = cast(_backend.fallback.asanyarray)
+ascontiguousarray = cast(_backend.fallback.ascontiguousarray)
+copy = cast(_backend.fallback.copy)
+frombuffer = cast(lambda *a, **k: _backend.fallback.array(np.frombuffer(*a, **k)))
+fromfile = cast(lambda *a, **k: _backend.fallback.array(np.fromfile(*a, **k)))
+fromfunction = cast(lambda *a, **k: _backend.fallback.array(np.fromfunction(*a, **k)))
+fromiter = cast(lambda *a, **k: _backend.fallback.array(np.fromiter(*a, **k)))
+loadtxt = cast(lambda *a, **k: _backend.fallback.array(np.loadtxt(*a, **k)))
+
+arange = cast(_backend.fallback.arange)                          # [delayarray.py:634-637]
+linspace = cast(_backend.fallback.linspace)
+logspace = cast(_backend.fallback.logspace)
+geomspace = cast(lambda *a, **k: _backend.fallback.array(np.geomspace(*a, **k)))
+
+tri = cast(_backend.fallback.tri)                                # [delayarray.py:641-644]
+tril = cast(_backend.fallback.tril)
+triu = cast(_backend.fallback.triu)
+vander = cast(lambda *a, **k: _backend.fallback.array(np.vander(*a, **k)))

@@ -1,0 +1,316 @@
+"""Device memory objects: DeviceBuffer (a pool allocation) and DeviceArray (a strided view).
+
+DeviceArray is the "backend ndarray" of the reference's backend-module protocol
+(SURVEY.md section 8b): what ``run(ex)`` returns and what ``is_ndarray`` recognises.  It supports
+``.get()`` (D2H; reference delayarray.py:101-106), ``.shape/.dtype/.astype/.reshape``, basic
+indexing as zero-copy views and slice assignment (delayarray.py:111-128) and ``str()``
+(delayarray.py:35-36).  It plays the part ``cupy.ndarray`` plays under the reference
+(cuda.py:21-26).
+"""
+import ctypes as C
+import weakref
+
+import numpy as np
+
+from . import _lib
+from ._lib import lib, check
+
+_current = {"dev": 0, "dry": False, "fake_ptr": 0x7F0000000000}
+
+
+def set_device(dev):
+    """Select the device new arrays are created on (one process per GPU: LOCAL_RANK)."""
+    _lib.init()
+    _current["dev"] = int(dev)
+
+
+def current_device():
+    return _current["dev"]
+
+
+def synchronize(dev=None):
+    check(lib.drc_device_sync(current_device() if dev is None else dev))
+
+
+class DeviceBuffer:
+    """One stream-ordered pool allocation.  ``ptr`` may be swapped (stencil ping-pong), every
+    view holds the buffer object, never the raw pointer.  ``version`` counts in-place writes
+    so memoised results that read this buffer can tell they are stale."""
+
+    __slots__ = ("ptr", "nbytes", "dev", "version", "__weakref__")
+
+    def __init__(self, nbytes, dev=None):
+        self.nbytes = int(nbytes)
+        self.version = 0
+        if _current["dry"]:
+            # planning / compile-only mode (no GPU): a 256-byte aligned placeholder address
+            # that is never dereferenced and never freed
+            self.dev = -1
+            self.ptr = _current["fake_ptr"]
+            _current["fake_ptr"] += (self.nbytes + 511) // 256 * 256
+            return
+        _lib.init()
+        self.dev = current_device() if dev is None else dev
+        p = C.c_uint64()
+        check(lib.drc_malloc_async(self.dev, 0, self.nbytes, C.byref(p)))
+        self.ptr = p.value
+
+    def __del__(self):
+        ptr, self.ptr = getattr(self, "ptr", 0), 0
+        if ptr and lib is not None and getattr(self, "dev", -1) >= 0:
+            try:
+                lib.drc_free_async(self.dev, 0, ptr)
+            except Exception:       # interpreter shutdown
+                pass
+
+    def swap_storage(self, other):
+        """Exchange the allocations of two equally sized buffers (ping-pong)."""
+        assert self.nbytes == other.nbytes and self.dev == other.dev
+        self.ptr, other.ptr = other.ptr, self.ptr
+        self.version += 1
+
+
+def _c_strides(shape, itemsize):
+    st, acc = [], itemsize
+    for n in reversed(shape):
+        st.append(acc)
+        acc *= max(n, 1)
+    return tuple(reversed(st))
+
+
+class DeviceArray:
+    """N-d strided view of a DeviceBuffer (strides and offset in bytes, NumPy convention)."""
+
+    __slots__ = ("buf", "offset", "shape", "strides", "dtype", "__weakref__")
+    __array_priority__ = 50.0
+
+    def __init__(self, buf, shape, dtype, strides=None, offset=0):
+        self.buf = buf
+        self.shape = tuple(int(s) for s in shape)
+        self.dtype = np.dtype(dtype)
+        self.strides = _c_strides(self.shape, self.dtype.itemsize) if strides is None \
+            else tuple(int(s) for s in strides)
+        self.offset = int(offset)
+
+    # ---- construction
+    @classmethod
+    def empty(cls, shape, dtype, dev=None):
+        if isinstance(shape, (int, np.integer)):
+            shape = (int(shape),)
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape, dtype=np.int64)) if len(shape) else 1
+        return cls(DeviceBuffer(n * dtype.itemsize, dev), shape, dtype)
+
+    @classmethod
+    def from_host(cls, host, dev=None, stream=0):
+        host = np.ascontiguousarray(host)
+        arr = cls.empty(host.shape, host.dtype, dev)
+        if host.nbytes and arr.dev >= 0:
+            check(lib.drc_memcpy_h2d_async(arr.dev, stream, arr.ptr, host.ctypes.data, host.nbytes))
+            if stream == 0:
+                # pageable source: the driver has consumed it when the call returns only for
+                # small copies; keep the contract simple and wait.
+                check(lib.drc_stream_sync(arr.dev, 0))
+        return arr
+
+    # ---- geometry
+    @property
+    def dev(self):
+        return self.buf.dev
+
+    @property
+    def ptr(self):
+        return self.buf.ptr + self.offset
+
+    @property
+    def ndim(self):
+        return len(self.shape)
+
+    @property
+    def size(self):
+        n = 1
+        for s in self.shape:
+            n *= s
+        return n
+
+    @property
+    def itemsize(self):
+        return self.dtype.itemsize
+
+    @property
+    def nbytes(self):
+        return self.size * self.dtype.itemsize
+
+    @property
+    def is_contiguous(self):
+        if self.size <= 1:
+            return True
+        acc = self.dtype.itemsize
+        for n, st in zip(reversed(self.shape), reversed(self.strides)):
+            if n != 1 and st != acc:
+                return False
+            acc *= n
+        return True
+
+    def layout_key(self):
+        """Identity of the viewed memory: equal keys == same elements (used for hash-consing
+        views, so the same slice taken twice is one graph leaf)."""
+        return (id(self.buf), self.offset, self.shape, self.strides, self.dtype.str)
+
+    def __len__(self):
+        return self.shape[0]
+
+    # ---- views (no kernels)
+    def _shadow(self):
+        base = np.empty(1, dtype=self.dtype)
+        return base, np.lib.stride_tricks.as_strided(base, self.shape, self.strides)
+
+    def __getitem__(self, key):
+        if isinstance(key, DeviceArray):
+            raise NotImplementedError("advanced (array) indexing is not supported on device arrays")
+        if isinstance(key, tuple) and any(isinstance(k, (np.ndarray, list, DeviceArray)) for k in key) \
+                or isinstance(key, (np.ndarray, list)):
+            raise NotImplementedError("advanced (array) indexing is not supported on device arrays")
+        base, shadow = self._shadow()
+        if not isinstance(key, tuple):
+            key = (key,)
+        if not any(k is Ellipsis for k in key):
+            key = key + (Ellipsis,)   # always a view object, never a dereferenced scalar
+        view = shadow[key]            # pure stride arithmetic on a 1-element shadow
+        off = view.__array_interface__["data"][0] - base.__array_interface__["data"][0]
+        return DeviceArray(self.buf, view.shape, self.dtype, view.strides, self.offset + off)
+
+    def reshape(self, *shape, **kw):
+        if len(shape) == 1 and isinstance(shape[0], (tuple, list)):
+            shape = tuple(shape[0])
+        src = self if self.is_contiguous else self.copy()
+        shape = _resolve_shape(src.size, shape)
+        return DeviceArray(src.buf, shape, src.dtype, None, src.offset)
+
+    def ravel(self):
+        return self.reshape(-1)
+
+    @property
+    def T(self):
+        return DeviceArray(self.buf, self.shape[::-1], self.dtype, self.strides[::-1], self.offset)
+
+    def transpose(self, *axes):
+        if not axes or axes == (None,):
+            return self.T
+        if len(axes) == 1 and isinstance(axes[0], (tuple, list)):
+            axes = tuple(axes[0])
+        return DeviceArray(self.buf, [self.shape[a] for a in axes], self.dtype,
+                           [self.strides[a] for a in axes], self.offset)
+
+    def broadcast_to(self, shape):
+        nd = len(shape)
+        shp = (1,) * (nd - self.ndim) + self.shape
+        st = (0,) * (nd - self.ndim) + self.strides
+        out = []
+        for want, have, s in zip(shape, shp, st):
+            if have == want:
+                out.append(s)
+            elif have == 1:
+                out.append(0)
+            else:
+                raise ValueError(f"cannot broadcast {self.shape} to {shape}")
+        return DeviceArray(self.buf, shape, self.dtype, out, self.offset)
+
+    # ---- data movement
+    def get(self, out=None, stream=0):
+        """Device -> host copy (reference: cupy.ndarray.get via delayarray.py:101-106)."""
+        src = self if self.is_contiguous else self.copy()
+        host = np.empty(src.shape, dtype=src.dtype) if out is None else out
+        assert host.flags.c_contiguous and host.nbytes == src.nbytes
+        if src.nbytes:
+            check(lib.drc_memcpy_d2h_async(src.dev, stream, host.ctypes.data, src.ptr, src.nbytes))
+        check(lib.drc_stream_sync(src.dev, stream))
+        return host
+
+    def __array__(self, dtype=None, copy=None):
+        host = self.get()
+        return host if dtype is None else host.astype(dtype)
+
+    def copy(self):
+        from . import engine
+        return engine.materialize_view(self)
+
+    def astype(self, dtype, copy=True):
+        dtype = np.dtype(dtype)
+        if dtype == self.dtype and not copy:
+            return self
+        from . import engine
+        return engine.cast_array(self, dtype)
+
+    def fill(self, value):
+        from . import engine
+        engine.assign(self, value)
+
+    def __setitem__(self, key, value):
+        from . import engine
+        target = self if (isinstance(key, type(Ellipsis)) or key == slice(None)) else self[key]
+        engine.assign(target, value)
+
+    def item(self):
+        return self.get().item()
+
+    def __float__(self):
+        return float(self.get())
+
+    def __int__(self):
+        return int(self.get())
+
+    def __bool__(self):
+        return bool(self.get())
+
+    def __str__(self):
+        return str(self.get())
+
+    def __repr__(self):
+        return f"DeviceArray(shape={self.shape}, dtype={self.dtype}, dev={self.dev})"
+
+
+def _resolve_shape(size, shape):
+    shape = [int(s) for s in shape]
+    if shape.count(-1) > 1:
+        raise ValueError("can only specify one unknown dimension")
+    known = 1
+    for s in shape:
+        if s != -1:
+            known *= s
+    if -1 in shape:
+        if known == 0 or size % known:
+            raise ValueError(f"cannot reshape array of size {size} into shape {tuple(shape)}")
+        shape[shape.index(-1)] = size // known
+    elif known != size:
+        raise ValueError(f"cannot reshape array of size {size} into shape {tuple(shape)}")
+    return tuple(shape)
+
+
+# ---- pinned host staging (e2e path)
+class _Pinned:
+    def __init__(self, nbytes):
+        _lib.init()
+        p = C.c_void_p()
+        check(lib.drc_host_alloc(nbytes, C.byref(p)))
+        self.ptr, self.nbytes = p.value, nbytes
+
+    def __del__(self):
+        if getattr(self, "ptr", None) and lib is not None:
+            try:
+                lib.drc_host_free(self.ptr)
+            except Exception:
+                pass
+
+
+def pinned_empty(shape, dtype):
+    """A NumPy array backed by page-locked host memory (fast, truly asynchronous copies)."""
+    dtype = np.dtype(dtype)
+    if isinstance(shape, (int, np.integer)):
+        shape = (int(shape),)
+    n = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
+    block = _Pinned(max(n, 1))
+    raw = (C.c_uint8 * max(n, 1)).from_address(block.ptr)
+    arr = np.frombuffer(raw, dtype=dtype, count=n // dtype.itemsize).reshape(shape)
+    raw._drc_block = block          # arr.base -> raw -> block: freed with the array
+    return arr

@@ -1,0 +1,630 @@
+"""Execution engine: plan -> generate -> compile (cubin cache) -> launch.
+
+Replaces ``cuda.run`` of the reference (cuda.py:91-96: emit, make_kernel, kern(*inputs)).
+The cubin cache has two levels: an in-process table keyed by the region's *structural* key
+(program + layout class, never sizes / pointers / scalar values) and an on-disk cache keyed
+by sha256(source + options); steady state is one dict lookup and one ctypes launch.
+All launches go through libdrcuda (include/drcuda.h); a missing GPU raises.
+"""
+import ctypes as C
+import hashlib
+import os
+import weakref
+
+import numpy as np
+
+from . import _lib, codegen, planner
+from ._lib import check, lib
+from .device import DeviceArray, DeviceBuffer, current_device
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+ARCH = "sm_100a"
+NVRTC_OPTIONS = [f"--gpu-architecture={ARCH}", "--std=c++17", "--fmad=false",
+                 "--generate-line-info", "-default-device"]
+CACHE_DIR = os.environ.get("DR_CACHE_DIR", os.path.join(_HERE, "_cache"))
+DUMP_SRC = os.environ.get("DR_DUMP_SRC")
+
+with open(os.path.join(_HERE, "csrc", "prelude.cuh")) as _f:
+    PRELUDE = _f.read()
+
+stats = {"compiled": 0, "disk_hits": 0, "mem_hits": 0, "launches": 0, "compile_ms": 0.0}
+
+
+# --------------------------------------------------------------------------- kernels
+class Kernel:
+    __slots__ = ("name", "source", "cubin", "funcs", "meta", "occ")
+
+    def __init__(self, name, source, cubin, meta):
+        self.name, self.source, self.cubin, self.meta = name, source, cubin, meta
+        self.funcs = {}           # device -> CUfunction handle
+        self.occ = {}
+
+    def func(self, dev):
+        f = self.funcs.get(dev)
+        if f is None:
+            mod, fn = C.c_uint64(), C.c_uint64()
+            check(lib.drc_module_load(dev, self.cubin, len(self.cubin), C.byref(mod)))
+            check(lib.drc_module_get_function(dev, mod, self.name.encode(), C.byref(fn)))
+            f = self.funcs[dev] = fn.value
+        return f
+
+    def blocks_per_sm(self, dev, threads, smem=0):
+        k = (dev, threads, smem)
+        v = self.occ.get(k)
+        if v is None:
+            out = C.c_int()
+            check(lib.drc_occupancy(dev, self.func(dev), threads, smem, C.byref(out)))
+            v = self.occ[k] = max(out.value, 1)
+        return v
+
+
+_kernels = {}
+
+
+def kernel_name(key):
+    return "dr_" + hashlib.sha256(repr(key).encode()).hexdigest()[:20]
+
+
+def compile_source(name, body_source):
+    """Source text -> cubin through the on-disk cache (works without a GPU)."""
+    import time
+    source = PRELUDE + "\n" + body_source
+    digest = hashlib.sha256((source + "\0" + " ".join(NVRTC_OPTIONS)).encode()).hexdigest()
+    path = os.path.join(CACHE_DIR, f"{name}-{digest[:16]}.cubin")
+    if os.path.exists(path):
+        with open(path, "rb") as f:
+            stats["disk_hits"] += 1
+            return source, f.read()
+    t0 = time.perf_counter()
+    cubin, _log = _lib.compile_cubin(source, name + ".cu", NVRTC_OPTIONS)
+    stats["compile_ms"] += (time.perf_counter() - t0) * 1e3
+    stats["compiled"] += 1
+    os.makedirs(CACHE_DIR, exist_ok=True)
+    tmp = f"{path}.{os.getpid()}.tmp"
+    with open(tmp, "wb") as f:
+        f.write(cubin)
+    os.replace(tmp, path)
+    if DUMP_SRC:
+        os.makedirs(DUMP_SRC, exist_ok=True)
+        with open(os.path.join(DUMP_SRC, name + ".cu"), "w") as f:
+            f.write(source)
+    return source, cubin
+
+
+def get_kernel(key, generate, meta=None):
+    """``generate(name) -> CUDA source`` is only called on a structural-key miss."""
+    k = _kernels.get(key)
+    if k is not None:
+        stats["mem_hits"] += 1
+        return k
+    name = kernel_name(key)
+    source, cubin = compile_source(name, generate(name))
+    k = _kernels[key] = Kernel(name, source, cubin, meta or {})
+    return k
+
+
+# --------------------------------------------------------------------------- device state
+class _DevState:
+    def __init__(self, dev):
+        sm, major, minor, l2, smem = C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        total = C.c_size_t()
+        check(lib.drc_device_attr(dev, C.byref(sm), C.byref(major), C.byref(minor),
+                                  C.byref(total), C.byref(l2), C.byref(smem)))
+        self.sm_count, self.cc, self.l2_bytes = sm.value, (major.value, minor.value), l2.value
+        self.max_smem = smem.value
+        self.total_mem = total.value
+        if self.cc[0] < 10:
+            raise _lib.DrcError(f"device {dev} is sm_{major.value}{minor.value}; this engine "
+                                f"targets {ARCH} only")
+        self.scratch = DeviceBuffer(MAX_PARTIALS * 16 + 256, dev)
+        check(lib.drc_memset_async(dev, 0, self.scratch.ptr, 0, self.scratch.nbytes))
+
+    @property
+    def partials_ptr(self):
+        return self.scratch.ptr + 256
+
+    @property
+    def counter_ptr(self):
+        return self.scratch.ptr
+
+
+MAX_PARTIALS = 8192
+_dev_state = {}
+dry_log = []          # (kernel, grid, block) recorded instead of launched in dry mode
+
+
+class _DryState:
+    """Stand-in device description for compile-only planning (no GPU in the build container)."""
+    sm_count, cc, l2_bytes, max_smem, total_mem = 148, (10, 0), 126 << 20, 232448, 180 << 30
+    partials_ptr, counter_ptr = 0x7E0000000100, 0x7E0000000000
+
+
+class dry_run:
+    """Context manager: plan, generate and NVRTC-compile regions without touching a device.
+    Arrays get placeholder addresses; launches are recorded in ``dry_log``.  Used by the CPU
+    test-suite and by __graft_entry__.build() to pre-compile the workload kernels."""
+
+    def __enter__(self):
+        from . import device
+        self._prev = device._current["dry"]
+        device._current["dry"] = True
+        return dry_log
+
+    def __exit__(self, *exc):
+        from . import device
+        device._current["dry"] = self._prev
+
+
+def is_dry():
+    from . import device
+    return device._current["dry"]
+
+
+def dev_state(dev):
+    if dev < 0:
+        return _DryState
+    st = _dev_state.get(dev)
+    if st is None:
+        _lib.init()
+        st = _dev_state[dev] = _DevState(dev)
+    return st
+
+
+# --------------------------------------------------------------------------- launch
+_PACK_ALIGN = 8
+
+
+class Args:
+    """Packs kernel arguments into one blob + offsets (drc_launch_packed)."""
+
+    __slots__ = ("buf", "offsets")
+
+    def __init__(self):
+        self.buf = bytearray()
+        self.offsets = []
+
+    def _align(self, a):
+        pad = (-len(self.buf)) % a
+        if pad:
+            self.buf += b"\0" * pad
+
+    def raw(self, data, align):
+        self._align(align)
+        self.offsets.append(len(self.buf))
+        self.buf += data
+
+    def i64(self, v):
+        self.raw(int(v).to_bytes(8, "little", signed=True), 8)
+
+    def ptr(self, v):
+        self.raw(int(v).to_bytes(8, "little", signed=False), 8)
+
+    def f64(self, v):
+        self.raw(np.float64(v).tobytes(), 8)
+
+    def scalar(self, value, dtype):
+        data = np.asarray(value, dtype=dtype).tobytes()
+        self.raw(data, max(len(data), 1))
+
+
+def launch(kernel, dev, grid, block, args, smem=0, stream=0, cluster=1):
+    if dev < 0:
+        dry_log.append((kernel, grid, block))
+        return
+    blob = bytes(args.buf)
+    offs = (C.c_uint32 * len(args.offsets))(*args.offsets)
+    gx, gy, gz = (tuple(grid) + (1, 1))[:3] if not isinstance(grid, int) else (grid, 1, 1)
+    bx, by, bz = (tuple(block) + (1, 1))[:3] if not isinstance(block, int) else (block, 1, 1)
+    check(lib.drc_launch_packed(dev, stream, kernel.func(dev), gx, gy, gz, bx, by, bz, smem,
+                                cluster, blob, offs, len(args.offsets)))
+    stats["launches"] += 1
+
+
+def _grid_for(kernel, dev, threads, work_items):
+    st = dev_state(dev)
+    cap = st.sm_count * (kernel.blocks_per_sm(dev, threads) if dev >= 0 else 8)
+    need = max(1, -(-work_items // threads))
+    return min(need, cap)
+
+
+# --------------------------------------------------------------------------- regions
+def _stamp_of(prog):
+    return [(weakref.ref(b), b.version) for b in prog.leaf_bufs]
+
+
+def _geo_blob(total, shape, strides_per_operand):
+    vals = [total] + list(shape)
+    for st in strides_per_operand:
+        vals += list(st)
+    return np.asarray(vals, dtype=np.int64).tobytes()
+
+
+def run_program(prog, outs, reduce=None, inplace=False):
+    """Launch the fused kernel of ``prog``.  ``outs``: DeviceArrays to write (elementwise), or
+    [] with ``reduce`` = (op, acc_dt, res_dt, count, result DeviceArray) for a full reduction."""
+    dev = outs[0].dev if outs else (prog.arrays[0].dev if prog.arrays else current_device())
+    st = dev_state(dev)
+    lay = planner.resolve_layout(prog, outs)
+    if lay.total == 0:
+        return
+    out_dts = tuple(o.dtype for o in outs)
+    red_key = None if reduce is None else (reduce[0], reduce[1].str, reduce[2].str)
+    moved = sum(a.dtype.itemsize for a, c in zip(prog.arrays, lay.in_class) if c != "b") \
+        + sum(o.dtype.itemsize for o in outs)
+    stream_hint = (not inplace) and lay.total * max(moved, 1) > 2 * st.l2_bytes
+    if lay.family == "flat":
+        key = ("flat", prog.key(), lay.in_class, tuple(d.str for d in out_dts), lay.vec_ok,
+               stream_hint, red_key, inplace)
+        gen_reduce = None if reduce is None else (reduce[0], reduce[1], reduce[2], None)
+        kern = get_kernel(key, lambda name: codegen.gen_flat(
+            name, prog, lay.in_class, out_dts, lay.vec_ok, stream_hint, gen_reduce))
+        a = Args()
+        a.i64(lay.total)
+        for arr in prog.arrays:
+            a.ptr(arr.ptr)
+        for val, dt in prog.scalars:
+            a.scalar(val, dt)
+        for o in outs:
+            a.ptr(o.ptr)
+        widest = max([x.dtype.itemsize for x, c in zip(prog.arrays, lay.in_class) if c == "c"]
+                     + [d.itemsize for d in out_dts] + [1])
+        vec = max(1, 16 // widest) if lay.vec_ok else 1
+        grid = _grid_for(kern, dev, 256, -(-lay.total // vec))
+    else:
+        wide = lay.total >= (1 << 32) or any(
+            abs(s) * n >= (1 << 62) for stv in lay.in_strides for s, n in zip(stv, lay.shape))
+        key = ("nd", prog.key(), len(lay.shape), lay.in_class, tuple(d.str for d in out_dts),
+               red_key, wide)
+        gen_reduce = None if reduce is None else (reduce[0], reduce[1], reduce[2], None)
+        kern = get_kernel(key, lambda name: codegen.gen_nd(
+            name, prog, len(lay.shape), lay.in_class, out_dts, gen_reduce, wide_index=wide))
+        a = Args()
+        operands = list(lay.in_strides) + (list(lay.out_strides) if reduce is None else [])
+        if not operands:
+            operands = [(0,) * len(lay.shape)]
+        a.raw(_geo_blob(lay.total, lay.shape, operands), 8)
+        for arr in prog.arrays:
+            a.ptr(arr.ptr)
+        for val, dt in prog.scalars:
+            a.scalar(val, dt)
+        for o in outs:
+            a.ptr(o.ptr)
+        grid = _grid_for(kern, dev, 256, lay.total)
+    if reduce is not None:
+        grid = min(grid, MAX_PARTIALS)
+        a.ptr(st.partials_ptr)
+        a.ptr(st.counter_ptr)
+        a.ptr(reduce[4].ptr)
+        a.f64(reduce[3])
+    launch(kern, dev, grid, 256, a)
+
+
+def evaluate_nodes(nodes, outs=None, inplace=False):
+    """Fuse ``nodes`` (same iteration shape) into one kernel; returns the output arrays."""
+    prog = planner.build_program(nodes)
+    if outs is None:
+        dev = prog.arrays[0].dev if prog.arrays else current_device()
+        outs = [DeviceArray.empty(prog.shape, n.dtype, dev) for n in nodes]
+    else:
+        prog.shape = tuple(outs[0].shape)
+    run_program(prog, outs, inplace=inplace)
+    stamp = _stamp_of(prog)
+    return outs, stamp
+
+
+def run(node):
+    """Backend protocol entry: evaluate one node, return its DeviceArray  (cuda.py:91-96)."""
+    kind = node.kind
+    if kind == "leaf":
+        return node._force()
+    if kind == "scalar":
+        raise TypeError("cannot evaluate a bare Scalar")
+    if kind == "ewise":
+        outs, stamp = evaluate_nodes([node])
+        node._stamp = stamp
+        return outs[0]
+    if kind == "reduce":
+        return _run_reduce(node)
+    if kind == "matmul":
+        return _run_contraction(node)
+    raise NotImplementedError(kind)
+
+
+def run_many(nodes):
+    """Co-evaluate: elementwise nodes sharing a shape go into ONE multi-output kernel."""
+    from .delayarray import _stamp_valid
+    groups = {}
+    for n in nodes:
+        if n.kind == "ewise" and not (n.__dict__.get("array") is not None and _stamp_valid(n._stamp)):
+            groups.setdefault(tuple(n.shape), [])
+            if all(n is not m for m in groups[tuple(n.shape)]):
+                groups[tuple(n.shape)].append(n)
+        else:
+            n._force()
+    for group in groups.values():
+        outs, stamp = evaluate_nodes(group)
+        for n, o in zip(group, outs):
+            n.array, n._stamp = o, stamp
+
+
+# --------------------------------------------------------------------------- reductions
+def _group_strides(arr_strides, shape, lo, hi):
+    """Collapse dims [lo, hi) of one operand to a single stride, or None if impossible."""
+    dims = [d for d in range(lo, hi) if shape[d] != 1]
+    if not dims:
+        return 0
+    for a, b in zip(dims, dims[1:]):
+        if arr_strides[a] != arr_strides[b] * shape[b]:
+            return None
+    return arr_strides[dims[-1]]
+
+
+def _run_reduce(node):
+    from .delayarray import NPArray, ReduceEx
+    child = node.children[0]
+    op = node.op
+    res_dt = node.dtype
+    nd = child.ndim
+    axes = node.axes
+    count = 1
+    for ax in axes:
+        count *= child.shape[ax]
+    post = float(count) if node.post == "mean" else 1.0
+    src = child
+    if src.dtype != res_dt:
+        src = child.astype(res_dt)          # e.g. bool/int8 sums accumulate as int64
+    acc_dt = codegen.acc_dtype(op, res_dt)
+    full = len(axes) == nd
+    # non-contiguous axis groups: peel the last contiguous run first
+    if not full and axes and any(b != a + 1 for a, b in zip(axes, axes[1:])):
+        run_start = len(axes) - 1
+        while run_start > 0 and axes[run_start - 1] == axes[run_start] - 1:
+            run_start -= 1
+        inner = ReduceEx(node.func, child, tuple(axes[run_start:]), True)
+        outer = ReduceEx(node.func, inner, tuple(axes[:run_start]), True)
+        res = outer._force()
+        if node.post == "mean":
+            res = (NPArray(res) / float(count)).astype(res_dt)._force()
+        return res.reshape(node.shape)
+    prog = planner.build_program([src])
+    prog.shape = tuple(child.shape)
+    dev = prog.arrays[0].dev if prog.arrays else current_device()
+    result = DeviceArray.empty(node.shape, res_dt, dev)
+    node._stamp = _stamp_of(prog)
+    if child.size == 0:
+        result.fill(0)
+        return result
+    if full or not axes:
+        if not axes:        # reduction over nothing: a copy
+            outs, _ = evaluate_nodes([src], [result])
+            return result
+        run_program(prog, [], reduce=(op, acc_dt, res_dt, post, result))
+        return result
+    lo, hi = axes[0], axes[-1] + 1
+    shape = child.shape
+    outer = int(np.prod(shape[:lo], dtype=np.int64))
+    red = int(np.prod(shape[lo:hi], dtype=np.int64))
+    inner = int(np.prod(shape[hi:], dtype=np.int64))
+    triples = []
+    for arr in prog.arrays:
+        bst = planner.broadcast_strides(arr, shape)
+        t = (_group_strides(bst, shape, 0, lo), _group_strides(bst, shape, lo, hi),
+             _group_strides(bst, shape, hi, nd))
+        if None in t:
+            triples = None
+            break
+        triples.append(t)
+    if triples is None:
+        # an operand whose dims do not collapse into (outer, reduced, inner): materialise the
+        # producer contiguously once, then reduce that
+        dense = NPArray(evaluate_nodes([src])[0][0])
+        return _run_reduce_dense(node, dense, outer, red, inner, op, acc_dt, res_dt, post, result)
+    _launch_axis_reduce(prog, triples, outer, red, inner, op, acc_dt, res_dt, post, result, dev)
+    return result
+
+
+def _run_reduce_dense(node, dense, outer, red, inner, op, acc_dt, res_dt, post, result):
+    prog = planner.build_program([dense])
+    item = dense.dtype.itemsize
+    triples = [(red * inner * item, inner * item, item)]
+    _launch_axis_reduce(prog, triples, outer, red, inner, op, acc_dt, res_dt, post, result,
+                        result.dev)
+    return result
+
+
+def _launch_axis_reduce(prog, triples, outer, red, inner, op, acc_dt, res_dt, post, result, dev):
+    st = dev_state(dev)
+    in_class = tuple("b" if t == (0, 0, 0) else "s" for t in triples)
+    red_spec = (op, acc_dt, res_dt, None)
+    a = Args()
+    n_ops = max(len(triples), 1)
+    pad = [(0, 0, 0)] * (n_ops - len(triples))
+    tr = list(triples) + pad
+    if inner == 1:
+        mode = "block" if red >= 2048 or outer < st.sm_count * 8 else "warp"
+        key = ("rows", prog.key(), in_class, op, acc_dt.str, res_dt.str, mode)
+        kern = get_kernel(key, lambda name: codegen.gen_rows(name, prog, in_class, red_spec, mode))
+        geo = [outer, red] + [t[0] for t in tr] + [t[1] for t in tr] + [res_dt.itemsize]
+        a.raw(np.asarray(geo, dtype=np.int64).tobytes(), 8)
+        for arr in prog.arrays:
+            a.ptr(arr.ptr)
+        for val, dt in prog.scalars:
+            a.scalar(val, dt)
+        a.ptr(result.ptr)
+        a.f64(post)
+        cap = st.sm_count * (kern.blocks_per_sm(dev, 256) if dev >= 0 else 8)
+        grid = min(outer, cap) if mode == "block" else min(max(1, -(-outer * 32 // 256)), cap)
+        launch(kern, dev, grid, 256, a)
+    else:
+        key = ("cols", prog.key(), in_class, op, acc_dt.str, res_dt.str)
+        kern = get_kernel(key, lambda name: codegen.gen_cols(name, prog, in_class, red_spec))
+        geo = [outer, red, inner] + [t[0] for t in tr] + [t[1] for t in tr] + [t[2] for t in tr]
+        a.raw(np.asarray(geo, dtype=np.int64).tobytes(), 8)
+        for arr in prog.arrays:
+            a.ptr(arr.ptr)
+        for val, dt in prog.scalars:
+            a.scalar(val, dt)
+        a.ptr(result.ptr)
+        a.f64(post)
+        launch(kern, dev, _grid_for(kern, dev, 256, outer * inner), 256, a)
+
+
+# --------------------------------------------------------------------------- contractions
+def _run_contraction(node):
+    from .delayarray import BinaryNumpyEx, DotEx, MVEx, ReduceEx
+    a, b = node.arg1, node.arg2
+    if isinstance(node, DotEx):
+        red = ReduceEx(np.add, BinaryNumpyEx(np.multiply, a, b), None, False)
+        out = red._force()
+        node._stamp = red._stamp
+        return out if out.dtype == node.dtype else out.astype(node.dtype)
+    if isinstance(node, MVEx):
+        red = ReduceEx(np.add, BinaryNumpyEx(np.multiply, a, b), 1, False)
+        out = red._force()
+        node._stamp = red._stamp
+        return out if out.dtype == node.dtype else out.astype(node.dtype)
+    return _run_matmul(node)
+
+
+def _run_matmul(node):
+    """A(M,K) @ B(K,N) with both operands' elementwise producers fused: iteration space
+    (M, K, N), reduced over K.  One thread per output element, B coalesced along N, A
+    broadcast within the warp.  (Round-1 functional path; the tcgen05 tile kernel for large
+    dense operands is the next row)"""
+    a, b = node.arg1, node.arg2
+    m, k = a.shape
+    n = b.shape[1]
+    res_dt = node.dtype
+    pa = planner.build_program([a if a.dtype == res_dt else a.astype(res_dt)])
+    pb = planner.build_program([b if b.dtype == res_dt else b.astype(res_dt)])
+    prog = planner.Program()
+    triples = []
+    remap = {}
+    for tag, p, dims in (("A", pa, (m, k)), ("B", pb, (k, n))):
+        base_a, base_s, base_t = len(prog.arrays), len(prog.scalars), len(prog.instrs)
+        for arr in p.arrays:
+            bst = planner.broadcast_strides(arr, dims)
+            triples.append((bst[0], bst[1], 0) if tag == "A" else (0, bst[0], bst[1]))
+            prog.arrays.append(arr)
+        prog.scalars += p.scalars
+
+        def mv(r, base_a=base_a, base_s=base_s, base_t=base_t):
+            return (r[0], r[1] + {"a": base_a, "s": base_s, "t": base_t}[r[0]])
+        for op, loop, out, args in p.instrs:
+            prog.instrs.append((op, loop, out, tuple(mv(r) for r in args)))
+        for r, dt in p.dtypes.items():
+            prog.dtypes[mv(r)] = dt
+        remap[tag] = mv(p.roots[0])
+        for buf in p.leaf_bufs:
+            if all(buf is not x for x in prog.leaf_bufs):
+                prog.leaf_bufs.append(buf)
+    prod = ("t", len(prog.instrs))
+    prog.instrs.append(("multiply", (res_dt, res_dt), res_dt, (remap["A"], remap["B"])))
+    prog.dtypes[prod] = res_dt
+    prog.roots = [prod]
+    dev = prog.arrays[0].dev if prog.arrays else current_device()
+    result = DeviceArray.empty((m, n), res_dt, dev)
+    node._stamp = _stamp_of(prog)
+    if m * n == 0:
+        return result
+    if k == 0:
+        result.fill(0)
+        return result
+    _launch_axis_reduce(prog, triples, m, k, n, "sum", codegen.acc_dtype("sum", res_dt), res_dt,
+                        1.0, result, dev)
+    return result
+
+
+# --------------------------------------------------------------------------- assignment / copies
+def _overlaps(a, b):
+    """Conservative: two views of one buffer whose byte extents intersect."""
+    if a.buf is not b.buf:
+        return False
+
+    def extent(x):
+        lo = hi = x.offset
+        for n, s in zip(x.shape, x.strides):
+            if n == 0:
+                return (0, 0)
+            if s >= 0:
+                hi += (n - 1) * s
+            else:
+                lo += (n - 1) * s
+        return lo, hi + x.dtype.itemsize
+    (alo, ahi), (blo, bhi) = extent(a), extent(b)
+    return alo < bhi and blo < ahi
+
+
+def assign(target, value):
+    """target[...] = value with NumPy semantics  (reference delayarray.py:114-121: force the
+    RHS into a temporary, then copy).  Here the RHS expression is fused and written straight
+    into the target view; a temporary is used only when the RHS reads the target's buffer at
+    *other* elements than the one being written (e.g. shifted stencil views)."""
+    from .delayarray import DelayArray, NPArray, Scalar, arg_to_numpy_ex
+    from numbers import Number
+    if isinstance(value, Number):
+        node = Scalar(value)
+        src = node if node.weak_type is None else Scalar(target.dtype.type(value))
+    elif isinstance(value, DelayArray):
+        src = value
+    else:
+        src = arg_to_numpy_ex(value if isinstance(value, (DeviceArray, np.ndarray))
+                              else np.asarray(value))
+    if src.kind in ("reduce", "matmul"):
+        src = NPArray(src._force())
+    if src.kind != "scalar":
+        np.broadcast_shapes(src.shape, target.shape)          # raises on mismatch
+        if len(src.shape) > target.ndim or np.broadcast_shapes(src.shape, target.shape) != target.shape:
+            raise ValueError(f"could not broadcast input array from shape {src.shape} "
+                             f"into shape {target.shape}")
+    if target.size == 0:
+        return
+    prog = planner.build_program([src]) if src.kind != "scalar" else _scalar_program(src)
+    prog.shape = tuple(target.shape)
+    tkey = (target.offset, planner.broadcast_strides(target, target.shape))
+    hazard, inplace = False, False
+    for arr in prog.arrays:
+        if arr.buf is target.buf and _overlaps(arr, target):
+            if (arr.offset, planner.broadcast_strides(arr, target.shape)) == tkey \
+                    and arr.dtype == target.dtype:
+                inplace = True
+            else:
+                hazard = True
+    if hazard:
+        tmp = DeviceArray.empty(target.shape, target.dtype, target.dev)
+        run_program(prog, [tmp])
+        p2 = planner.build_program([NPArray(tmp)])
+        p2.shape = tuple(target.shape)
+        run_program(p2, [target])
+    else:
+        run_program(prog, [target], inplace=inplace)
+    target.buf.version += 1
+
+
+def _scalar_program(node):
+    prog = planner.Program()
+    prog.scalars.append((node.val, node.dtype))
+    prog.dtypes[("s", 0)] = node.dtype
+    prog.roots = [("s", 0)]
+    return prog
+
+
+def materialize_view(arr):
+    """Contiguous copy of a (possibly strided) DeviceArray."""
+    from .delayarray import NPArray
+    outs, _ = evaluate_nodes([NPArray(arr)])
+    return outs[0]
+
+
+def cast_array(arr, dtype):
+    from .delayarray import CastEx, NPArray
+    outs, _ = evaluate_nodes([CastEx(NPArray(arr), dtype)])
+    return outs[0]
+
+
+def cumsum(arr, axis=None):
+    raise NotImplementedError("cumsum: device scan kernel not implemented yet")
+
+
+def synchronize(dev=None):
+    check(lib.drc_device_sync(current_device() if dev is None else dev))

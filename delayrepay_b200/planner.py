@@ -1,0 +1,209 @@
+"""DAG -> fused-region planner (replaces the reference's tree-walking Visitor, visitor.py:4-24,
+and the statement-list construction of CupyEmitter, cuda.py:46-88).
+
+One *program* per fused region: an SSA list over typed operands, built by an ITERATIVE
+post-order walk of the DAG (each node once -- no Python recursion, no exponential re-walk of
+shared sub-expressions), with value numbering on top of the capture layer's
+hash-consing.  Operand and temporary names are positional, never the global node counter, so
+structurally equal expressions produce byte-identical source and hit the cubin cache
+(the reference recompiles every new expression object).
+
+Cut points: reductions, contractions and already materialised nodes become region inputs.
+Layout resolution: every array operand is broadcast to the iteration shape and all operands
+are collapsed jointly to the fewest dimensions; the result picks the kernel family
+("flat" = one contiguous vectorised dimension, "nd" = general strided/broadcast).
+"""
+import numpy as np
+
+from .device import DeviceArray
+
+
+class Program:
+    """SSA program of one fused region.
+
+    arrays : list of DeviceArray        -- array operands, in first-use order
+    scalars: list of (value, np.dtype)  -- typed scalar kernel arguments
+    instrs : list of (op, loop_dtypes, out_dtype, args); args are ('a', i) | ('s', j) | ('t', k)
+    roots  : list of operand refs, one per requested output
+    """
+
+    __slots__ = ("arrays", "scalars", "instrs", "roots", "shape", "leaf_bufs", "dtypes")
+
+    def __init__(self):
+        self.arrays, self.scalars, self.instrs, self.roots = [], [], [], []
+        self.shape = ()
+        self.leaf_bufs = []
+        self.dtypes = {}            # operand ref -> np.dtype
+
+    def key(self):
+        """Structure only: no sizes, pointers or scalar values."""
+        return (tuple(a.dtype.str for a in self.arrays),
+                tuple(dt.str for _, dt in self.scalars),
+                tuple((op, tuple(d.str for d in loop), out.str, args)
+                      for op, loop, out, args in self.instrs),
+                tuple(self.roots))
+
+
+def _is_materialised(node):
+    from .delayarray import _stamp_valid
+    return node.__dict__.get("array") is not None and _stamp_valid(node._stamp)
+
+
+def build_program(roots):
+    """Linearise the elementwise DAG under ``roots`` (list of nodes) into a Program."""
+    prog = Program()
+    ref = {}                 # id(node) -> operand ref
+    array_slot = {}          # layout key -> index into prog.arrays
+    scalar_slot = {}         # (id(node), dtype) -> index into prog.scalars
+    value_no = {}            # (op, loop, args) -> temp ref
+
+    def array_operand(node, dev_arr):
+        lk = dev_arr.layout_key()
+        idx = array_slot.get(lk)
+        if idx is None:
+            idx = array_slot[lk] = len(prog.arrays)
+            prog.arrays.append(dev_arr)
+        r = ("a", idx)
+        prog.dtypes[r] = dev_arr.dtype
+        ref[id(node)] = r
+
+    def scalar_operand(node, dtype):
+        k = (id(node), dtype.str)
+        idx = scalar_slot.get(k)
+        if idx is None:
+            idx = scalar_slot[k] = len(prog.scalars)
+            prog.scalars.append((dtype.type(node.val), dtype))
+        r = ("s", idx)
+        prog.dtypes[r] = dtype
+        return r
+
+    stack = [(r, False) for r in reversed(roots)]
+    while stack:
+        node, expanded = stack.pop()
+        if id(node) in ref:
+            continue
+        kind = node.kind
+        if kind == "scalar":
+            continue                       # typed at each use
+        if kind == "leaf":
+            array_operand(node, node._force())
+            continue
+        if kind in ("reduce", "matmul") or (not expanded and _is_materialised(node)):
+            array_operand(node, node._force())      # cut point: evaluate (or reuse) first
+            continue
+        if not expanded:
+            stack.append((node, True))
+            for kid in reversed(node.children):
+                if id(kid) not in ref:
+                    stack.append((kid, False))
+            continue
+        args = []
+        for kid, loop_dt in zip(node.children, node.loop):
+            if kid.kind == "scalar":
+                args.append(scalar_operand(kid, kid.dtype if kid.weak_type is None else loop_dt))
+            else:
+                args.append(ref[id(kid)])
+        args = tuple(args)
+        vn = (node.op, node.loop, node.dtype, args)
+        hit = value_no.get(vn)
+        if hit is None:
+            hit = value_no[vn] = ("t", len(prog.instrs))
+            prog.instrs.append((node.op, node.loop, node.dtype, args))
+            prog.dtypes[hit] = node.dtype
+        ref[id(node)] = hit
+
+    prog.roots = [ref[id(r)] for r in roots]
+    prog.shape = tuple(np.broadcast_shapes(*[r.shape for r in roots])) if roots else ()
+    seen = set()
+    for a in prog.arrays:
+        if id(a.buf) not in seen:
+            seen.add(id(a.buf))
+            prog.leaf_bufs.append(a.buf)
+    return prog
+
+
+# --------------------------------------------------------------------------- layout
+def broadcast_strides(arr, shape):
+    """Byte strides of ``arr`` viewed at iteration shape ``shape`` (0 on broadcast dims)."""
+    nd = len(shape)
+    shp = (1,) * (nd - arr.ndim) + tuple(arr.shape)
+    st = (0,) * (nd - arr.ndim) + tuple(arr.strides)
+    out = []
+    for want, have, s in zip(shape, shp, st):
+        if have == want and want != 1:
+            out.append(s)
+        elif have == 1 or want == 1:
+            out.append(0)
+        else:
+            raise ValueError(f"operand of shape {arr.shape} does not broadcast to {shape}")
+    return tuple(out)
+
+
+def collapse(shape, strides_list):
+    """Jointly collapse dimensions: drop size-1 dims, merge dims that are contiguous for
+    every operand.  Returns (shape, [strides per operand]); at least one dimension."""
+    dims = [i for i, n in enumerate(shape) if n != 1]
+    if not dims:
+        return (1,), [(0,) for _ in strides_list]
+    shp = [shape[i] for i in dims]
+    sts = [[st[i] for i in dims] for st in strides_list]
+    out_shape, out_sts = [shp[0]], [[st[0]] for st in sts]
+    for d in range(1, len(shp)):
+        n = shp[d]
+        if all(o[-1] == st[d] * n for o, st in zip(out_sts, sts)):
+            out_shape[-1] *= n
+            for o, st in zip(out_sts, sts):
+                o[-1] = st[d]
+        else:
+            out_shape.append(n)
+            for o, st in zip(out_sts, sts):
+                o.append(st[d])
+    return tuple(out_shape), [tuple(o) for o in out_sts]
+
+
+class Layout:
+    """Resolved geometry of one region launch."""
+
+    __slots__ = ("shape", "in_strides", "out_strides", "family", "in_class", "vec_ok", "total")
+
+    def key(self):
+        return (self.family, len(self.shape), self.in_class, self.vec_ok)
+
+
+def resolve_layout(prog, outs):
+    """Pick the kernel family for program ``prog`` writing into DeviceArrays ``outs``."""
+    shape = prog.shape
+    ins = [broadcast_strides(a, shape) for a in prog.arrays]
+    out_st = [broadcast_strides(o, shape) for o in outs]
+    cshape, csts = collapse(shape, ins + out_st)
+    lay = Layout()
+    lay.shape = cshape
+    lay.in_strides = csts[:len(ins)]
+    lay.out_strides = csts[len(ins):]
+    lay.total = 1
+    for n in cshape:
+        lay.total *= n
+    flat = len(cshape) == 1
+    cls = []
+    if flat:
+        for a, st in zip(prog.arrays, lay.in_strides):
+            if st[0] == a.dtype.itemsize:
+                cls.append("c")                 # contiguous, walks with the index
+            elif st[0] == 0:
+                cls.append("b")                 # broadcast scalar: one load per thread
+            else:
+                flat = False
+        for o, st in zip(outs, lay.out_strides):
+            if st[0] != o.dtype.itemsize:
+                flat = False
+    if flat:
+        aligned = all(a.ptr % 16 == 0 for a, c in zip(prog.arrays, cls) if c == "c") and \
+            all(o.ptr % 16 == 0 for o in outs)
+        lay.family = "flat"
+        lay.in_class = tuple(cls)
+        lay.vec_ok = bool(aligned)
+    else:
+        lay.family = "nd"
+        lay.in_class = tuple("b" if all(s == 0 for s in st) else "s" for st in lay.in_strides)
+        lay.vec_ok = False
+    return lay

@@ -1,0 +1,338 @@
+"""Parity of the CUDA path against the oracle (oracle/refcpu.py == the reference's CPU backend)
+on identical seeded inputs, and against the committed golden fixtures.
+
+Bars (BASELINE.json north_star): elementwise arithmetic BIT-EXACT; transcendentals <= 2 ulp;
+reductions rtol 1e-12 (fp64) / 1e-5 (fp32).  Chains that mix both (Black-Scholes, n-body) are
+held to a bound derived from those (stated where used) and must be at least as accurate as the
+reference against a float64 evaluation.
+"""
+import os
+
+import numpy as np
+import pytest
+from scipy.special import erf
+
+from delayrepay_b200 import workloads as wl
+from oracle import refcpu
+from util import assert_bits_equal, assert_ulp, ulp_distance
+
+pytestmark = pytest.mark.gpu
+GOLDEN = np.load(os.path.join(os.path.dirname(__file__), "golden", "workloads.npz"))
+EPS32 = float(np.finfo(np.float32).eps)
+
+
+# ------------------------------------------------------------------ C1: axpy, bit-exact
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 255, 2048, (1 << 20) + 3, 1 << 24])
+def test_axpy_bit_exact(gpu, n):
+    i = wl.make_inputs("axpy", n)
+    got = wl.axpy(gpu, i["a"], gpu.array(i["x"]), gpu.array(i["y"])).get()
+    want = wl.axpy(refcpu, i["a"], refcpu.leaf(i["x"]), refcpu.leaf(i["y"])).get()
+    assert_bits_equal(got, want, f"axpy n={n}")
+    if n == 2048:
+        assert_bits_equal(got, GOLDEN["axpy"], "axpy golden")
+
+
+def test_axpy_unaligned_and_strided_views_bit_exact(gpu):
+    i = wl.make_inputs("axpy", 10007)
+    x, y = gpu.array(i["x"]), gpu.array(i["y"])
+    for sl in (slice(1, None), slice(3, -2), slice(None, None, 2), slice(None, None, -1),
+               slice(5, 9001, 3)):
+        got = (1.5 * x[sl] + y[sl]).get()
+        assert_bits_equal(got, 1.5 * i["x"][sl] + i["y"][sl], f"slice {sl}")
+
+
+# ------------------------------------------------------------------ arithmetic, bit-exact
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_arithmetic_chain_bit_exact(gpu, dt):
+    rng = np.random.default_rng(11)
+    a, b, c = (rng.standard_normal(100003).astype(dt) for _ in range(3))
+    c = np.abs(c) + dt(0.5)
+
+    def f(xp, a, b, c):
+        return (a * b + c) / (c - a * 0.25) - xp.sqrt(c) * (a - b) / c + abs(a) * 3
+    got = f(gpu, gpu.array(a), gpu.array(b), gpu.array(c)).get()
+    want = f(refcpu, refcpu.leaf(a), refcpu.leaf(b), refcpu.leaf(c)).get()
+    assert_bits_equal(got, want, "arith chain")
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_integer_power_chain_matches_reference_association(gpu, dt):
+    rng = np.random.default_rng(6)
+    if dt is np.float64:
+        rng.standard_normal(2048)
+    x = rng.standard_normal(2048).astype(dt)
+    name = np.dtype(dt).name
+    assert_bits_equal((gpu.array(x) ** 3).get(), GOLDEN[f"pow3_{name}"], "x**3")
+    assert_bits_equal((gpu.array(x) ** 5).get(), GOLDEN[f"pow5_{name}"], "x**5")
+    assert_bits_equal((gpu.array(x) ** 2).get(), x * x, "x**2")
+    assert_bits_equal(np.square(gpu.array(x)).get(), np.square(x), "square")
+
+
+def test_scalar_typing_follows_nep50(gpu):
+    x = np.random.default_rng(3).standard_normal(4099).astype(np.float32)
+    assert_bits_equal((gpu.array(x) * 0.1).get(), x * 0.1, "f32 * python float")
+    assert_bits_equal((gpu.array(x) * np.float64(0.1)).get(), x * np.float64(0.1), "f32 * f64")
+    assert_bits_equal((gpu.array(x) + 7).get(), x + 7, "f32 + int")
+    xi = np.arange(-50, 50, dtype=np.int64)
+    assert_bits_equal((gpu.array(xi) * 0.5).get(), xi * 0.5, "i64 * float")
+    assert_bits_equal((gpu.array(xi) / 3).get(), xi / 3, "i64 / int")
+    assert_bits_equal((gpu.array(xi) // 7).get(), xi // 7, "i64 // int")
+    assert_bits_equal((gpu.array(xi) % 7).get(), xi % 7, "i64 % int")
+    assert_bits_equal((gpu.array(x) > 0.25).get(), x > 0.25, "compare")
+    assert_bits_equal(gpu.array(x).astype(np.float64).get(), x.astype(np.float64), "astype")
+    inf = gpu.array(x) * float("inf")
+    assert_bits_equal(inf.get(), x * float("inf"), "inf scalar (a literal would not compile)")
+
+
+# ------------------------------------------------------------------ transcendentals, <= 2 ulp
+UNARY = [("exp", np.exp, (-20, 20)), ("log", np.log, (1e-3, 1e3)), ("sin", np.sin, (-20, 20)),
+         ("cos", np.cos, (-20, 20)), ("tan", np.tan, (-1.5, 1.5)), ("tanh", np.tanh, (-5, 5)),
+         ("sinh", np.sinh, (-8, 8)), ("cosh", np.cosh, (-8, 8)), ("erf", erf, (-4, 4)),
+         ("sqrt", np.sqrt, (0, 1e6)), ("arctan", np.arctan, (-50, 50)),
+         ("log1p", np.log1p, (-0.9, 10)), ("expm1", np.expm1, (-5, 5))]
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("name,fn,rng_", UNARY, ids=[u[0] for u in UNARY])
+def test_transcendental_within_2ulp(gpu, dt, name, fn, rng_):
+    x = np.random.default_rng(17).uniform(rng_[0], rng_[1], 1 << 20).astype(dt)
+    got = fn(gpu.array(x)).get()
+    want = fn(x)
+    assert got.dtype == want.dtype
+    worst = assert_ulp(got, want, 0 if name == "sqrt" else 2, f"{name} {np.dtype(dt).name}")
+    print(f"{name:6s} {np.dtype(dt).name}: max {worst} ulp, "
+          f"{(ulp_distance(got, want) == 0).mean():.4f} bit-identical")
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_binary_functions_within_2ulp(gpu, dt):
+    rng = np.random.default_rng(19)
+    a = rng.uniform(0.1, 50, 1 << 18).astype(dt)
+    b = rng.uniform(-3, 3, 1 << 18).astype(dt)
+    assert_ulp(np.arctan2(gpu.array(b), gpu.array(a)).get(), np.arctan2(b, a), 2, "arctan2")
+    assert_ulp(np.power(gpu.array(a), gpu.array(b)).get(), np.power(a, b), 2, "power")
+    assert_ulp((gpu.array(a) ** -1.5).get(), a ** -1.5, 2, "x**-1.5")
+    assert_ulp((gpu.array(a) ** 0.5).get(), a ** 0.5, 0, "x**0.5")
+    assert_ulp(np.hypot(gpu.array(a), gpu.array(b)).get(), np.hypot(a, b), 2, "hypot")
+    assert_bits_equal(np.maximum(gpu.array(a), gpu.array(b)).get(), np.maximum(a, b), "maximum")
+
+
+def test_special_values(gpu):
+    x = np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 1e-45, -1e-45, 3.4e38, 88.8, -104.0, 1.0],
+                 dtype=np.float32)
+    with np.errstate(all="ignore"):
+        for fn in (np.exp, np.log, np.sqrt, np.tanh, erf, np.abs, np.negative, np.sign):
+            got, want = fn(gpu.array(x)).get(), fn(x)
+            assert np.array_equal(np.isnan(got), np.isnan(want)), fn.__name__
+            assert_ulp(got, want, 2, fn.__name__)
+        assert_bits_equal(np.maximum(gpu.array(x), 0.5).get(), np.maximum(x, np.float32(0.5)), "max nan")
+        assert_bits_equal(np.isnan(gpu.array(x)).get(), np.isnan(x), "isnan")
+        assert_bits_equal((gpu.array(x) / gpu.array(x[::-1].copy())).get(), x / x[::-1], "div")
+
+
+# ------------------------------------------------------------------ C2: Black-Scholes
+def _bs_truth(S, K, T, r=0.02, v=0.30):
+    S, K, T = (a.astype(np.float64) for a in (S, K, T))
+    return wl.black_scholes(np, S, K, T, r, v)
+
+
+@pytest.mark.parametrize("n", [2048, (1 << 20) + 1])
+def test_black_scholes_parity(gpu, n):
+    i = wl.make_inputs("black_scholes", n)
+    call, put = wl.black_scholes(gpu, *(gpu.array(i[k]) for k in ("S", "K", "T")))
+    gpu.evaluate(call, put)
+    rc, rp = wl.black_scholes(refcpu, *(refcpu.leaf(i[k]) for k in ("S", "K", "T")))
+    tc, tp = _bs_truth(i["S"], i["K"], i["T"])
+    # every op but log/exp/erf is exact; those three are <= 2 ulp from NumPy's, and a 1-ulp
+    # difference in any of them moves call/put by at most a few ulp OF THE OPERAND SCALE
+    # max(S, K) (the result is a difference of two terms that large), hence this bound:
+    scale = 16 * EPS32 * np.maximum(i["S"], i["K"])
+    for nm, got, want, truth in (("call", call.get(), rc.get(), tc), ("put", put.get(), rp.get(), tp)):
+        assert got.dtype == np.float32
+        assert np.all(np.abs(got.astype(np.float64) - want) <= scale), nm
+        err_got = np.abs(got - truth).mean()
+        err_ref = np.abs(want - truth).mean()
+        assert err_got <= 1.05 * err_ref + 1e-9, (nm, err_got, err_ref)
+        print(f"{nm}: bit-identical to NumPy {np.mean(got == want):.3f}; mean |err| vs f64 "
+              f"ours {err_got:.3e} reference {err_ref:.3e}")
+    if n == 2048:
+        assert np.all(np.abs(call.get() - GOLDEN["bs_call"]) <= scale)
+        assert np.all(np.abs(put.get() - GOLDEN["bs_put"]) <= scale)
+
+
+def test_black_scholes_separately_forced_equals_coevaluated(gpu):
+    i = wl.make_inputs("black_scholes", 5000)
+    c1, p1 = wl.black_scholes(gpu, *(gpu.array(i[k]) for k in ("S", "K", "T")))
+    a, b = c1.get(), p1.get()                       # two kernels, as a reference user would
+    gpu.reset()
+    c2, p2 = wl.black_scholes(gpu, *(gpu.array(i[k]) for k in ("S", "K", "T")))
+    gpu.evaluate(c2, p2)                            # one two-output kernel
+    assert_bits_equal(a, c2.get(), "call")
+    assert_bits_equal(b, p2.get(), "put")
+
+
+# ------------------------------------------------------------------ C3: fused reductions
+@pytest.mark.parametrize("n", [1, 7, 2048, (1 << 22) + 5])
+def test_l2_dot_norm_fp64_rtol_1e12(gpu, n):
+    i = wl.make_inputs("l2", n)
+    a, b = gpu.array(i["a"]), gpu.array(i["b"])
+    ra, rb = refcpu.leaf(i["a"]), refcpu.leaf(i["b"])
+    for nm, got, want in (
+            ("l2", wl.l2_distance(gpu, a, b), wl.l2_distance(refcpu, ra, rb)),
+            ("dot", wl.dot(gpu, a, b), wl.dot(refcpu, ra, rb).get()),
+            ("norm", wl.norm(gpu, a), np.sqrt(wl.dot(refcpu, ra, ra).get()))):
+        got = got.get()
+        assert got.dtype == np.float64 and got.shape == ()
+        scale = max(abs(float(want)), np.sqrt(n) * 1e-3)      # dot of random signs cancels
+        assert abs(float(got) - float(want)) <= 1e-12 * scale, (nm, got, want)
+    if n == 2048:
+        np.testing.assert_allclose(wl.l2_distance(gpu, a, b).get(), GOLDEN["l2"], rtol=1e-12)
+        np.testing.assert_allclose(wl.dot(gpu, a, b).get(), GOLDEN["dot"], rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(wl.norm(gpu, a).get(), GOLDEN["norm"], rtol=1e-12)
+
+
+def test_reductions_fp32_rtol_1e5_and_exact_cases(gpu):
+    rng = np.random.default_rng(23)
+    x = rng.uniform(0, 1, (1 << 21) + 3).astype(np.float32)
+    X = gpu.array(x)
+    np.testing.assert_allclose(np.sum(X).get(), np.sum(x), rtol=1e-5)
+    np.testing.assert_allclose(np.mean(X).get(), np.mean(x), rtol=1e-5)
+    assert np.sum(X).dtype == np.float32
+    assert_bits_equal(np.max(X).get(), np.max(x), "max")
+    assert_bits_equal(np.min(X).get(), np.min(x), "min")
+    xi = rng.integers(-1000, 1000, 100001)
+    assert_bits_equal(np.sum(gpu.array(xi)).get(), np.sum(xi), "int sum")
+    assert_bits_equal(np.sum(gpu.array(xi > 0)).get(), np.sum(xi > 0), "bool sum")
+    assert_bits_equal(gpu.sum(gpu.full((64,), 7).astype(np.float32)).get(), np.float32(448.0), "ref test_sum")
+    np.testing.assert_allclose(np.var(X).get(), np.var(x), rtol=1e-5)
+    np.testing.assert_allclose(np.linalg.norm(X).get(), np.linalg.norm(x), rtol=1e-5)
+
+
+def test_axis_reductions(gpu):
+    rng = np.random.default_rng(29)
+    m = rng.standard_normal((37, 53, 11))
+    M = gpu.array(m)
+    for axis in (0, 1, 2, -1, (1, 2), (0, 1), (0, 2), None):
+        np.testing.assert_allclose(np.sum(M, axis=axis).get(), np.sum(m, axis=axis), rtol=1e-12, atol=1e-12)
+        assert_bits_equal(np.max(M, axis=axis).get(), np.max(m, axis=axis), f"max axis={axis}")
+    np.testing.assert_allclose(np.mean(M, axis=1, keepdims=True).get(), np.mean(m, axis=1, keepdims=True), rtol=1e-12)
+    big = rng.standard_normal((3, 50000)).astype(np.float32)
+    np.testing.assert_allclose(np.sum(gpu.array(big), axis=1).get(), np.sum(big, axis=1), rtol=1e-5, atol=1e-3)
+    np.testing.assert_allclose(np.sum(gpu.array(big), axis=0).get(), np.sum(big, axis=0), rtol=1e-5, atol=1e-5)
+    lazy = np.sum((M * 2.0 + 1.0) ** 2, axis=2)       # producer fused into the row reduction
+    np.testing.assert_allclose(lazy.get(), np.sum((m * 2.0 + 1.0) ** 2, axis=2), rtol=1e-12)
+
+
+# ------------------------------------------------------------------ C4: heat stencil, bit-exact
+@pytest.mark.parametrize("shape,steps", [((64, 64), 5), ((130, 257), 7), ((3, 3), 2), ((1000, 1031), 3)])
+def test_heat_bit_exact(gpu, shape, steps):
+    rng = np.random.default_rng(4)
+    u0 = rng.random(shape, dtype=np.float32) if shape != (64, 64) else wl.make_inputs("heat", 64)["u"]
+    u = gpu.array(u0.copy())
+    wl.heat(gpu, u, steps)
+    want = wl.heat(refcpu, refcpu.leaf(u0.copy()), steps).get()
+    assert_bits_equal(u.get(), want, f"heat {shape}")
+    if shape == (64, 64):
+        assert_bits_equal(u.get(), GOLDEN["heat"], "heat golden")
+
+
+def test_heat_steps_reuse_one_kernel(gpu):
+    from delayrepay_b200 import engine
+    u = gpu.array(wl.make_inputs("heat", 96)["u"])
+    wl.heat(gpu, u, 2)
+    before = engine.stats["compiled"] + engine.stats["disk_hits"]
+    wl.heat(gpu, u, 10)
+    assert engine.stats["compiled"] + engine.stats["disk_hits"] == before
+
+
+# ------------------------------------------------------------------ C5: n-body
+@pytest.mark.parametrize("n", [128, 517])
+def test_nbody_parity(gpu, n):
+    i = wl.make_inputs("nbody", n)
+    got = wl.nbody_acc(gpu, gpu.array(i["pos"]), gpu.array(i["m"])).get()
+    want = np.asarray(wl.nbody_acc(refcpu, refcpu.leaf(i["pos"]), refcpu.leaf(i["m"])))
+    truth = wl.nbody_acc(np, i["pos"].astype(np.float64), i["m"].astype(np.float64))
+    assert got.shape == (n, 3) and got.dtype == np.float32
+    # acc = W@pos - pos*rowsum(W) cancels: tolerance is rtol 1e-5 of the terms' magnitude
+    w = i["m"][None, :] * ((i["pos"][:, None, :] - i["pos"][None, :, :]) ** 2).sum(-1).__add__(1e-3) ** -1.5
+    scale = (w[:, :, None] * np.abs(i["pos"])[None, :, :]).sum(1) + np.abs(i["pos"]) * w.sum(1)[:, None]
+    assert np.all(np.abs(got - want) <= 1e-5 * scale)
+    assert np.abs(got - truth).max() <= 1.5 * np.abs(want - truth).max() + 1e-5 * scale.max()
+    if n == 128:
+        assert np.all(np.abs(got - GOLDEN["nbody"]) <= 1e-5 * scale)
+
+
+# ------------------------------------------------------------------ semantics around the path
+def test_setitem_invalidates_memoised_results(gpu):
+    """SURVEY.md section 7 'stale results': the reference returns the OLD x + y after x[0] = 100."""
+    x, y = gpu.array(np.arange(8.0)), gpu.array(np.ones(8))
+    first = (x + y).get()
+    x[0] = 100.0
+    second = (x + y).get()
+    assert first[0] == 1.0 and second[0] == 101.0
+
+
+def test_views_alias_and_assign(gpu):
+    a0 = np.arange(48, dtype=np.float32).reshape(6, 8)
+    a = gpu.array(a0.copy())
+    row = a[2]
+    a[2, :] = -1.0
+    assert_bits_equal(row.get(), np.full(8, -1, np.float32), "view sees write")
+    a[1:4, ::2] = a[1:4, 1::2] * 2
+    b = a0.copy(); b[2, :] = -1; b[1:4, ::2] = b[1:4, 1::2] * 2
+    assert_bits_equal(a.get(), b, "strided assign")
+    a[:, 1:] = a[:, :-1]              # overlapping shifted self-assignment: temp semantics
+    b[:, 1:] = b[:, :-1].copy()
+    assert_bits_equal(a.get(), b, "overlap assign")
+    assert_bits_equal(a.T.get(), b.T, "transpose")
+    assert_bits_equal(a.reshape(8, 6).get(), b.reshape(8, 6), "reshape")
+    assert_bits_equal(a[::-1, ::-2].get(), b[::-1, ::-2], "negative strides")
+
+
+def test_broadcast_where_and_mixed_ops(gpu):
+    rng = np.random.default_rng(31)
+    m, v = rng.standard_normal((33, 65)), rng.standard_normal(65)
+    M, V = gpu.array(m), gpu.array(v)
+    assert_bits_equal((M + V).get(), m + v, "row broadcast")
+    assert_bits_equal((M * V[None, :] - M[:, :1]).get(), m * v[None, :] - m[:, :1], "col broadcast")
+    assert_bits_equal(np.where(M > 0, M, V).get(), np.where(m > 0, m, v), "where")
+    assert_bits_equal(np.where(M > 0, 1.0, -1.0).get(), np.where(m > 0, 1.0, -1.0), "where scalars")
+    assert_bits_equal(np.clip(M, -0.5, 0.5).get(), np.clip(m, -0.5, 0.5), "clip")
+    assert_bits_equal((V[:, None] - V[None, :]).get(), v[:, None] - v[None, :], "outer difference")
+    z = gpu.zeros((0, 5))
+    assert (z + 1).get().shape == (0, 5)
+    assert float(np.sum(z).get()) == 0.0
+    s = gpu.array(np.float64(3.0))
+    assert float((s * 2).get()) == 6.0
+
+
+def test_matvec_gemm_and_dot_variants(gpu):
+    """reference tests/test.py:114-140 (TestMatrix) and :87-100 (the vacuous dot tests, made real)."""
+    rng = np.random.default_rng(37)
+    a, b, v = (rng.standard_normal(s).astype(np.float32) for s in ((64, 48), (48, 40), (48,)))
+    A, B, V = gpu.array(a), gpu.array(b), gpu.array(v)
+    np.testing.assert_allclose((A @ V).get(), a @ v, rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose((A @ B).get(), a @ b, rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(np.dot(A, V).get(), a @ v, rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(A.dot(B).get(), a @ b, rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(((A * 2 + 1) @ (B - 1)).get(), (a * 2 + 1) @ (b - 1), rtol=1e-5, atol=1e-4)
+    x = gpu.full((64,), 7).astype(np.float32)
+    y = gpu.arange(64).astype(np.float32)
+    assert float(x.dot(y)) == float(np.full(64, 7, np.float32).dot(np.arange(64, dtype=np.float32)))
+    m = gpu.full((64, 64), 7).astype(np.float32)
+    assert_bits_equal((m @ m).get(), np.full((64, 64), 7, np.float32) @ np.full((64, 64), 7, np.float32), "test_gemm")
+
+
+def test_eager_helpers(gpu):
+    a0 = np.arange(24, dtype=np.float64).reshape(4, 6)
+    a = gpu.array(a0)
+    assert_bits_equal(np.roll(a, 2, axis=1).get(), np.roll(a0, 2, axis=1), "roll axis")
+    assert_bits_equal(np.roll(a, -5).get(), np.roll(a0, -5), "roll flat")
+    assert_bits_equal(np.repeat(a, 3, axis=0).get(), np.repeat(a0, 3, axis=0), "repeat")
+    assert_bits_equal(np.tile(a, (2, 3)).get(), np.tile(a0, (2, 3)), "tile")
+    assert_bits_equal(np.diag(a).get(), np.diag(a0), "diag")
+    assert_bits_equal(np.diagflat(a[0]).get(), np.diagflat(a0[0]), "diagflat")
+    assert_bits_equal(np.transpose(a).get(), a0.T, "transpose")
+    assert_bits_equal(gpu.linspace(0, 1, 11).get(), np.linspace(0, 1, 11), "linspace")
+    assert_bits_equal(gpu.eye(3).get(), np.eye(3), "eye")
+    assert gpu.pi == np.pi and gpu.random.rand(4, 3).shape == (4, 3)

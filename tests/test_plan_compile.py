@@ -1,0 +1,136 @@
+"""Host logic without a GPU: capture, hash-consing, planning, code generation and NVRTC
+compilation of every workload (engine.dry_run: placeholder addresses, launches recorded)."""
+import numpy as np
+import pytest
+
+import delayrepay_b200 as dr
+from delayrepay_b200 import engine, planner, workloads as wl
+
+
+@pytest.fixture()
+def dry():
+    with engine.dry_run() as log:
+        del log[:]
+        yield log
+
+
+def test_memoise_leaf_and_expression(dry):
+    """reference tests/test.py:143-162 (TestMeta)."""
+    arr = np.array([1, 2, 3])
+    assert dr.NPArray(arr) is dr.NPArray(arr)
+    a = dr.full((3,), 5).astype(np.float32)
+    b = dr.full((3,), 3).astype(np.float32)
+    assert a is not b
+    x = dr.array([1, 2, 3])
+    assert np.sin(x) is np.sin(x)
+    assert (x + 1) is (x + 1)
+    assert (x + 1) is not (x + 1.0)          # 1 / 1.0 / True no longer collide
+    assert (x * 2) is not (x * True)
+
+
+def test_dtype_promotion_follows_numpy(dry):
+    f32 = dr.array(np.ones(8, np.float32))
+    i64 = dr.array(np.ones(8, np.int64))
+    assert (f32 * 0.1).dtype == np.float32            # NEP 50: weak Python scalar
+    assert (f32 * np.float64(0.1)).dtype == np.float64
+    assert (i64 * 0.5).dtype == np.float64
+    assert (i64 / i64).dtype == np.float64
+    assert (f32 > 0.5).dtype == np.bool_
+    assert np.sqrt(i64).dtype == np.float64
+    assert (f32 + i64).dtype == np.float64
+    assert np.sum(dr.array(np.ones(4, np.int8))).dtype == np.int64
+    assert np.sum(f32).dtype == np.float32
+
+
+def test_broadcast_shapes_stay_lazy(dry):
+    x = dr.array(np.ones(5, np.float32))
+    d = x[None, :] - x[:, None]
+    assert isinstance(d, dr.DelayArray) and d.shape == (5, 5)
+    with pytest.raises(ValueError):
+        dr.array(np.ones(4)) + dr.array(np.ones(5))
+
+
+def test_integer_power_expands_left_associated(dry):
+    x = dr.array(np.ones(8))
+    p = x ** 3
+    assert isinstance(p, dr.BinaryNumpyEx) and p.op == "multiply"
+    assert p.children[1] is x and p.children[0].children[0] is x
+    assert (x ** 2.5).op == "power"
+    assert np.square(x) is x * x
+
+
+def test_unknown_ufunc_raises_keyerror(dry):
+    x = dr.array(np.ones(8))
+    with pytest.raises(KeyError):
+        np.spacing(x)
+    with pytest.raises(KeyError):
+        np.argsort(x)
+
+
+def test_structural_key_ignores_values_and_sizes(dry):
+    def plan(n, a):
+        x, y = dr.array(np.ones(n)), dr.array(np.ones(n))
+        return planner.build_program([a * x + y]).key()
+    assert plan(64, 2.0) == plan(4096, -7.5)
+    before = engine.stats["compiled"] + engine.stats["disk_hits"]
+    for n, a in ((64, 2.0), (4096, -7.5), (1 << 20, 0.1)):
+        x, y = dr.array(np.ones(n)), dr.array(np.ones(n))
+        (a * x + y).run()
+    assert engine.stats["compiled"] + engine.stats["disk_hits"] - before <= 1
+
+
+def test_shared_subexpressions_are_planned_once(dry):
+    x = dr.array(np.ones(64))
+    e = x
+    for _ in range(18):                 # 2^18 paths through the DAG; reference: 262143 statements
+        e = e + e
+    prog = planner.build_program([e])
+    assert len(prog.instrs) == 18
+
+
+def test_all_workloads_generate_and_compile(dry):
+    i = wl.make_inputs("axpy", 4096)
+    wl.axpy(dr, i["a"], dr.array(i["x"]), dr.array(i["y"])).run()
+    i = wl.make_inputs("black_scholes", 4096)
+    call, put = wl.black_scholes(dr, *(dr.array(i[k]) for k in ("S", "K", "T")))
+    n0 = len(dry)
+    dr.evaluate(call, put)
+    assert len(dry) == n0 + 1, "call and put must share ONE fused kernel"
+    kern = dry[-1][0]
+    assert kern.source.count("dr_erf(") >= 2 and "dr_ld<" in kern.source
+    i = wl.make_inputs("l2", 4096)
+    a, b = dr.array(i["a"]), dr.array(i["b"])
+    n0 = len(dry)
+    wl.dot(dr, a, b).run()
+    assert len(dry) == n0 + 1, "dot = multiply fused into the reduction kernel"
+    assert "dr_grid_reduce" in dry[-1][0].source
+    wl.l2_distance(dr, a, b).run()
+    wl.norm(dr, a).run()
+    u = dr.array(wl.make_inputs("heat", 64)["u"])
+    wl.heat(dr, u, 2)
+    i = wl.make_inputs("nbody", 64)
+    wl.nbody_acc(dr, dr.array(i["pos"]), dr.array(i["m"])).run()
+    for kern, grid, block in dry:
+        assert kern.cubin[:4] == b"\x7fELF"
+
+
+def test_cubin_is_sm100a_with_vector_ldst(dry, tmp_path):
+    import subprocess
+    x, y = dr.array(np.ones(1 << 12)), dr.array(np.ones(1 << 12))
+    (1.5 * x + y).run()
+    kern = dry[-1][0]
+    p = tmp_path / "k.cubin"
+    p.write_bytes(kern.cubin)
+    sass = subprocess.run(["cuobjdump", "-sass", str(p)], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass or "SM100a" in sass.upper() or "EF_CUDA_SM100" in sass
+    assert "LDG.E.128" in sass and "STG.E.128" in sass
+    assert "DFMA" not in sass, "fmad=false: a*x+y must not be contracted"
+
+
+def test_no_cpu_fallback_without_device():
+    from delayrepay_b200 import _lib
+    if _lib.gpu_available():
+        pytest.skip("a GPU is present")
+    x = dr.array(np.ones(8))               # host-backed leaf: graph building only
+    with pytest.raises(_lib.DrcError):
+        (x + 1).get()
