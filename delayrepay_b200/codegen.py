@@ -12,6 +12,8 @@ Kernel families
             matrix @ vector): one warp or one block per row, fused producer
 Everything is emitted with positional names so equal structure == equal source text.
 """
+import os
+
 import numpy as np
 
 CTYPE = {
@@ -45,8 +47,26 @@ _CALL2 = {"hypot", "copysign", "fmod", "fmax", "fmin", "remainder", "floor_divid
 _CALL2_RENAMED = {"arctan2": "atan2", "maximum": "max", "minimum": "min"}
 
 
-def emit_expr(op, loop, out_dt, args, arg_dts):
-    """C expression for one SSA instruction; ``args`` are C expressions of dtype arg_dts."""
+_FAST_F32 = {"true_divide": "dr_div_fast({0}, {1}, bad)", "divide": "dr_div_fast({0}, {1}, bad)",
+             "sqrt": "dr_sqrt_fast({0}, bad)", "log": "dr_log_fast({0}, bad)",
+             "reciprocal": "dr_div_fast(1.0f, {0}, bad)"}
+_HEAVY = {"exp", "log", "erf", "erfc", "sin", "cos", "tan", "power", "tanh", "sinh", "cosh",
+          "arctan2", "arctan", "arcsin", "arccos", "exp2", "expm1", "log1p", "log2", "log10",
+          "true_divide", "divide", "sqrt", "cbrt", "hypot"}
+
+
+def has_fast_path(prog):
+    """Does the program contain float32 ops whose precise form carries a slow-path branch?"""
+    return any(op in _FAST_F32 and loop[0] == np.float32 for op, loop, _, _ in prog.instrs)
+
+
+def body_weight(prog):
+    return sum(1 for op, _, _, _ in prog.instrs if op in _HEAVY)
+
+
+def emit_expr(op, loop, out_dt, args, arg_dts, fast=False):
+    """C expression for one SSA instruction; ``args`` are C expressions of dtype arg_dts.
+    ``fast``: use the branch-free flag-raising float32 forms (see prelude, dr_*_fast)."""
     cast_args = []
     for a, have, want in zip(args, arg_dts, loop):
         if have == want:
@@ -56,6 +76,8 @@ def emit_expr(op, loop, out_dt, args, arg_dts):
         else:
             cast_args.append(f"(({ctype(want)})({a}))")
     a = cast_args
+    if fast and op in _FAST_F32 and loop[0] == np.float32:
+        return _FAST_F32[op].format(*a)
     T = ctype(loop[0])
     k = loop[0].kind
     O = ctype(out_dt)
@@ -113,13 +135,14 @@ def _operand_name(ref):
     return {"a": "x", "s": "s", "t": "t"}[ref[0]] + str(ref[1])
 
 
-def emit_body(prog):
+def emit_body(prog, fast=False):
     """The fused scalar body: `const T tK = expr;` lines over x<i> (arrays), s<j> (scalars)."""
     lines = []
     for k, (op, loop, out_dt, args) in enumerate(prog.instrs):
         exprs = [_operand_name(r) for r in args]
         dts = [prog.dtypes[r] for r in args]
-        lines.append(f"const {ctype(out_dt)} t{k} = {emit_expr(op, loop, out_dt, exprs, dts)};")
+        lines.append(f"const {ctype(out_dt)} t{k} = "
+                     f"{emit_expr(op, loop, out_dt, exprs, dts, fast)};")
     return lines
 
 
@@ -158,18 +181,26 @@ def _identity(op, dt):
 # --------------------------------------------------------------------------- flat family
 def gen_flat(name, prog, in_class, out_dts, vec_ok, stream, reduce=None, unroll=None,
              threads=256, min_blocks=None):
-    """Contiguous 1-d kernel.  ``reduce`` = None or (op, acc np.dtype, result np.dtype, post)."""
+    """Contiguous 1-d kernel.  ``reduce`` = None or (op, acc np.dtype, result np.dtype, post).
+
+    One copy of the fused body per vector lane (plus one scalar-tail copy): each thread loads
+    U vectors of V elements (all loads first), evaluates them, stores them; U = 1 for heavy
+    bodies (their own arithmetic hides the memory latency and the loop has to fit the
+    instruction cache), up to 4 for streaming bodies (more bytes in flight per thread).
+    Float32 '/', sqrt and log run through their branch-free fast forms; a vector that raised
+    the exception flag is recomputed once through the precise forms."""
     arrays, scalars = prog.arrays, prog.scalars
-    n_in = len(arrays)
     item_sizes = [a.dtype.itemsize for a, c in zip(arrays, in_class) if c == "c"]
     item_sizes += [np.dtype(d).itemsize for d in out_dts] if reduce is None else []
     widest = max(item_sizes) if item_sizes else 4
     V = max(1, 16 // widest) if vec_ok else 1
     n_stream = sum(1 for c in in_class if c == "c") + (len(out_dts) if reduce is None else 0)
     if unroll is None:
-        unroll = 4 if n_stream <= 2 else (2 if n_stream <= 6 else 1)
+        unroll = int(os.environ.get("DR_UNROLL", 0)) or (
+            1 if body_weight(prog) >= 2 else (4 if n_stream <= 2 else 2))
     U = unroll
     S = "true" if stream else "false"
+    two_tier = has_fast_path(prog)
 
     params = ["const i64 n"]
     for i, a in enumerate(arrays):
@@ -185,9 +216,26 @@ def gen_flat(name, prog, in_class, out_dts, vec_ok, stream, reduce=None, unroll=
         params += [f"{A}* __restrict__ partials", "unsigned int* __restrict__ counter",
                    f"{ctype(res_dt)}* __restrict__ result", "const double post_scale"]
 
-    body = emit_body(prog)
+    safe_body = emit_body(prog, fast=False)
+    fast_body = emit_body(prog, fast=True) if two_tier else safe_body
     src = []
     w = src.append
+    if two_tier:
+        fp = [f"const {ctype(a.dtype)} x{i}" for i, a in enumerate(arrays)]
+        fp += [f"const {ctype(dt)} s{j}" for j, (_, dt) in enumerate(scalars)]
+        res_types = [ctype(dt) for dt in out_dts] if reduce is None else [A]
+        w(f"struct {name}_res {{ " + " ".join(f"{t} o{o};" for o, t in enumerate(res_types)) + " };")
+        w(f"__device__ __noinline__ {name}_res {name}_safe({', '.join(fp)}) {{")
+        for line in safe_body:
+            w(f"  {line}")
+        w(f"  {name}_res res;")
+        if reduce is None:
+            for o, (r, dt) in enumerate(zip(prog.roots, out_dts)):
+                w(f"  res.o{o} = {_store_expr(prog, r, dt)};")
+        else:
+            w(f"  res.o0 = ({A}){_operand_name(prog.roots[0])};")
+        w("  return res;")
+        w("}")
     lb = f"__launch_bounds__({threads}" + (f", {min_blocks})" if min_blocks else ")")
     w(f'extern "C" __global__ void {lb} {name}({", ".join(params)}) {{')
     for i, (a, c) in enumerate(zip(arrays, in_class)):
@@ -198,57 +246,78 @@ def gen_flat(name, prog, in_class, out_dts, vec_ok, stream, reduce=None, unroll=
         w(f"#pragma unroll\n  for (int u = 0; u < {U}; ++u) acc[u] = {_identity(rop, acc_dt)};")
     w(f"  const i64 nv = n / {V};")
     w("  const i64 stride = (i64)gridDim.x * blockDim.x;")
-    w("  i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;")
 
-    def trip(u_count, indent):
-        p = " " * indent
+    def element(body, p, target):
+        """One element: bind inputs, run `body`, deliver the root(s) to `target`."""
         for i, (a, c) in enumerate(zip(arrays, in_class)):
             if c == "c":
-                w(f"{p}Vec<{ctype(a.dtype)}, {V}> v{i}[{u_count}];")
-        w(f"{p}#pragma unroll")
-        w(f"{p}for (int u = 0; u < {u_count}; ++u) {{")
-        for i, (a, c) in enumerate(zip(arrays, in_class)):
-            if c == "c":
-                w(f"{p}  v{i}[u] = dr_ld<{S}, {ctype(a.dtype)}, {V}>(in{i} + (i + u * stride) * {V});")
-        w(f"{p}}}")
-        w(f"{p}#pragma unroll")
-        w(f"{p}for (int u = 0; u < {u_count}; ++u) {{")
-        if reduce is None:
-            for o, dt in enumerate(out_dts):
-                w(f"{p}  Vec<{ctype(dt)}, {V}> r{o};")
-        w(f"{p}  #pragma unroll")
-        w(f"{p}  for (int e = 0; e < {V}; ++e) {{")
-        for i, (a, c) in enumerate(zip(arrays, in_class)):
-            if c == "c":
-                w(f"{p}    const {ctype(a.dtype)} x{i} = v{i}[u].v[e];")
+                w(f"{p}const {ctype(a.dtype)} x{i} = v{i}[u].v[e];")
         for line in body:
-            w(f"{p}    {line}")
+            w(f"{p}{line}")
         if reduce is None:
             for o, (r, dt) in enumerate(zip(prog.roots, out_dts)):
-                w(f"{p}    r{o}.v[e] = {_store_expr(prog, r, dt)};")
+                w(f"{p}r{o}.v[e] = {_store_expr(prog, r, dt)};")
         else:
-            w(f"{p}    acc[u] = {_RED[rop]}::op(acc[u], ({A}){_operand_name(prog.roots[0])});")
-        w(f"{p}  }}")
-        if reduce is None:
-            for o, dt in enumerate(out_dts):
-                w(f"{p}  dr_st<{S}, {ctype(dt)}, {V}>(out{o} + (i + u * stride) * {V}, r{o});")
-        w(f"{p}}}")
+            w(f"{p}val[e] = ({A}){_operand_name(prog.roots[0])};")
 
-    if U > 1:
-        w(f"  for (; i + {U - 1} * stride < nv; i += {U} * stride) {{")
-        trip(U, 4)
-        w("  }")
-    w("  for (; i < nv; i += stride) {")
-    trip(1, 4)
+    w(f"  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += {U} * stride) {{")
+    for i, (a, c) in enumerate(zip(arrays, in_class)):
+        if c == "c":
+            w(f"    Vec<{ctype(a.dtype)}, {V}> v{i}[{U}];")
+    w("#pragma unroll")
+    w(f"    for (int u = 0; u < {U}; ++u) {{")
+    w("      const i64 iu = i + u * stride;")
+    w("      const i64 ic = iu < nv ? iu : nv - 1;       // idle slots re-read a valid vector")
+    for i, (a, c) in enumerate(zip(arrays, in_class)):
+        if c == "c":
+            w(f"      v{i}[u] = dr_ld<{S}, {ctype(a.dtype)}, {V}>(in{i} + ic * {V});")
+    w("    }")
+    w("#pragma unroll")
+    w(f"    for (int u = 0; u < {U}; ++u) {{")
+    if reduce is None:
+        for o, dt in enumerate(out_dts):
+            w(f"      Vec<{ctype(dt)}, {V}> r{o};")
+    else:
+        w(f"      {A} val[{V}];")
+    if two_tier:
+        w("      bool bad = false;")
+    w("#pragma unroll")
+    w(f"      for (int e = 0; e < {V}; ++e) {{")
+    element(fast_body, "        ", None)
+    w("      }")
+    if two_tier:
+        w("      if (bad) {                                 // rare: precise re-evaluation")
+        w("#pragma unroll")
+        w(f"        for (int e = 0; e < {V}; ++e) {{")
+        call_in = ", ".join([f"v{i}[u].v[e]" if c == "c" else f"x{i}"
+                             for i, c in enumerate(in_class)] + [f"s{j}" for j in range(len(scalars))])
+        w(f"          const {name}_res res = {name}_safe({call_in});")
+        if reduce is None:
+            for o in range(len(out_dts)):
+                w(f"          r{o}.v[e] = res.o{o};")
+        else:
+            w("          val[e] = res.o0;")
+        w("        }")
+        w("      }")
+    if reduce is None:
+        guard = "" if U == 1 else "if (i + u * stride < nv) "
+        for o, dt in enumerate(out_dts):
+            w(f"      {guard}dr_st<{S}, {ctype(dt)}, {V}>(out{o} + (i + u * stride) * {V}, r{o});")
+    else:
+        w(f"      if (i + u * stride < nv) {{")
+        w("#pragma unroll")
+        w(f"        for (int e = 0; e < {V}; ++e) acc[u] = {_RED[rop]}::op(acc[u], val[e]);")
+        w("      }")
+    w("    }")
     w("  }")
-    # scalar tail: n - nv*V < V elements, handled by the first threads of block 0
+    # scalar tail: the n - nv*V < V trailing elements, first threads of block 0, precise forms
     if V > 1:
         w(f"  if (blockIdx.x == 0 && threadIdx.x < (unsigned)(n - nv * {V})) {{")
         w(f"    const i64 j = nv * {V} + threadIdx.x;")
         for i, (a, c) in enumerate(zip(arrays, in_class)):
             if c == "c":
                 w(f"    const {ctype(a.dtype)} x{i} = in{i}[j];")
-        for line in body:
+        for line in safe_body:
             w(f"    {line}")
         if reduce is None:
             for o, (r, dt) in enumerate(zip(prog.roots, out_dts)):

@@ -77,6 +77,16 @@ def build_program(roots):
         prog.dtypes[r] = dtype
         return r
 
+    def emit(op, loop, out_dt, args):
+        vn = (op, loop, out_dt, args)
+        hit = value_no.get(vn)
+        if hit is None:
+            hit = value_no[vn] = ("t", len(prog.instrs))
+            prog.instrs.append((op, loop, out_dt, args))
+            prog.dtypes[hit] = out_dt
+        return hit
+
+    neg = {}                 # id(node) -> True when ref[id(node)] holds MINUS the node's value
     stack = [(r, False) for r in reversed(roots)]
     while stack:
         node, expanded = stack.pop()
@@ -97,22 +107,25 @@ def build_program(roots):
                 if id(kid) not in ref:
                     stack.append((kid, False))
             continue
-        args = []
+        args, negs = [], []
         for kid, loop_dt in zip(node.children, node.loop):
             if kid.kind == "scalar":
                 args.append(scalar_operand(kid, kid.dtype if kid.weak_type is None else loop_dt))
+                negs.append(False)
             else:
-                args.append(ref[id(kid)])
-        args = tuple(args)
-        vn = (node.op, node.loop, node.dtype, args)
-        hit = value_no.get(vn)
-        if hit is None:
-            hit = value_no[vn] = ("t", len(prog.instrs))
-            prog.instrs.append((node.op, node.loop, node.dtype, args))
-            prog.dtypes[hit] = node.dtype
-        ref[id(node)] = hit
+                r = ref[id(kid)]
+                args.append(r)
+                negs.append(neg.get(id(kid), False))
+        ref[id(node)], flag = _emit_signed(node, args, negs, emit)
+        if flag:
+            neg[id(node)] = True
 
-    prog.roots = [ref[id(r)] for r in roots]
+    prog.roots = []
+    for r in roots:
+        operand = ref[id(r)]
+        if neg.get(id(r), False):
+            operand = emit("negative", (r.dtype,), r.dtype, (operand,))
+        prog.roots.append(operand)
     prog.shape = tuple(np.broadcast_shapes(*[r.shape for r in roots])) if roots else ()
     seen = set()
     for a in prog.arrays:
@@ -120,6 +133,46 @@ def build_program(roots):
             seen.add(id(a.buf))
             prog.leaf_bufs.append(a.buf)
     return prog
+
+
+# --------------------------------------------------------------------------- sign hoisting
+_SIGN_PRODUCT = ("multiply", "true_divide", "divide")
+_ODD = ("erf",)              # f(-x) == -f(x) bit for bit in NumPy/SciPy and on the device
+
+
+def _emit_signed(node, args, negs, emit):
+    """Emit ``node`` with negations hoisted outwards: -x is never computed, the sign travels
+    as a flag through * and / ((-a)*b == -(a*b) exactly, zeros included), odd functions, and
+    is absorbed by + and - ((a) + (-b) == a - b is the IEEE definition).  Black-Scholes'
+    cnd(-d1), cnd(-d2) thereby reuse erf(d1), erf(d2): two erf evaluations instead of four,
+    with bit-identical results.  Cases that would change the sign of a zero sum
+    ((-a)+(-b) vs -(a+b)) are not rewritten."""
+    op, loop, dt = node.op, node.loop, node.dtype
+    plain = dt.kind == "f" and all(d == dt for d in loop)
+
+    def solid(i):
+        return emit("negative", (loop[i],), loop[i], (args[i],)) if negs[i] else args[i]
+
+    if plain and any(negs) or (plain and op == "negative"):
+        if op == "negative":
+            return args[0], not negs[0]
+        if op in _SIGN_PRODUCT:
+            return emit(op, loop, dt, tuple(args)), negs[0] != negs[1]
+        if op in _ODD:
+            return emit(op, loop, dt, tuple(args)), negs[0]
+        if op in ("absolute", "fabs"):
+            return emit(op, loop, dt, tuple(args)), False
+        if op == "add":
+            if negs == [False, True]:
+                return emit("subtract", loop, dt, (args[0], args[1])), False
+            if negs == [True, False]:
+                return emit("subtract", loop, dt, (args[1], args[0])), False
+        if op == "subtract":
+            if negs == [False, True]:
+                return emit("add", loop, dt, (args[0], args[1])), False
+            if negs == [True, True]:
+                return emit("subtract", loop, dt, (args[1], args[0])), False
+    return emit(op, loop, dt, tuple(solid(i) for i in range(len(args)))), False
 
 
 # --------------------------------------------------------------------------- layout

@@ -14,7 +14,8 @@ from scipy.special import erf
 
 from delayrepay_b200 import workloads as wl
 from oracle import refcpu
-from util import assert_bits_equal, assert_ulp, ulp_distance
+from util import (assert_bits_equal, assert_close_to_numpy_or_truth, assert_ulp, erf_exact,
+                  ulp_distance)
 
 pytestmark = pytest.mark.gpu
 GOLDEN = np.load(os.path.join(os.path.dirname(__file__), "golden", "workloads.npz"))
@@ -99,9 +100,20 @@ def test_transcendental_within_2ulp(gpu, dt, name, fn, rng_):
     got = fn(gpu.array(x)).get()
     want = fn(x)
     assert got.dtype == want.dtype
-    worst = assert_ulp(got, want, 0 if name == "sqrt" else 2, f"{name} {np.dtype(dt).name}")
-    print(f"{name:6s} {np.dtype(dt).name}: max {worst} ulp, "
-          f"{(ulp_distance(got, want) == 0).mean():.4f} bit-identical")
+    limit = 0 if name == "sqrt" else 2
+    d = ulp_distance(got, want)
+    print(f"{name:6s} {np.dtype(dt).name}: max {int(d.max())} ulp vs NumPy, "
+          f"{(d == 0).mean():.4f} bit-identical")
+    if dt is np.float64 and name == "erf" and d.max() > limit:
+        # two double erf implementations (CUDA libm: 2 ulp; SciPy/xsf: ~1 ulp) can be 3 apart;
+        # settle the disagreeing points against a 40-digit evaluation: ours must be <= 2 ulp
+        bad = np.flatnonzero(d > limit)[:64]
+        from decimal import Decimal
+        for i, t in zip(bad, erf_exact(x[bad])):
+            err = abs(Decimal(float(got[i])) - t) / Decimal(float(np.spacing(abs(got[i]))))
+            assert err <= 2, (x[i], float(err))
+        return
+    assert_close_to_numpy_or_truth(got, want, fn, (x,), limit, f"{name} {np.dtype(dt).name}")
 
 
 @pytest.mark.parametrize("dt", [np.float32, np.float64])
@@ -109,8 +121,10 @@ def test_binary_functions_within_2ulp(gpu, dt):
     rng = np.random.default_rng(19)
     a = rng.uniform(0.1, 50, 1 << 18).astype(dt)
     b = rng.uniform(-3, 3, 1 << 18).astype(dt)
-    assert_ulp(np.arctan2(gpu.array(b), gpu.array(a)).get(), np.arctan2(b, a), 2, "arctan2")
-    assert_ulp(np.power(gpu.array(a), gpu.array(b)).get(), np.power(a, b), 2, "power")
+    assert_close_to_numpy_or_truth(np.arctan2(gpu.array(b), gpu.array(a)).get(), np.arctan2(b, a),
+                                   np.arctan2, (b, a), 2, "arctan2")
+    assert_close_to_numpy_or_truth(np.power(gpu.array(a), gpu.array(b)).get(), np.power(a, b),
+                                   np.power, (a, b), 2, "power")
     assert_ulp((gpu.array(a) ** -1.5).get(), a ** -1.5, 2, "x**-1.5")
     assert_ulp((gpu.array(a) ** 0.5).get(), a ** 0.5, 0, "x**0.5")
     assert_ulp(np.hypot(gpu.array(a), gpu.array(b)).get(), np.hypot(a, b), 2, "hypot")
@@ -128,6 +142,28 @@ def test_special_values(gpu):
         assert_bits_equal(np.maximum(gpu.array(x), 0.5).get(), np.maximum(x, np.float32(0.5)), "max nan")
         assert_bits_equal(np.isnan(gpu.array(x)).get(), np.isnan(x), "isnan")
         assert_bits_equal((gpu.array(x) / gpu.array(x[::-1].copy())).get(), x / x[::-1], "div")
+
+
+def test_division_sqrt_log_on_random_bit_patterns(gpu):
+    """The branch-free fast paths + flagged precise re-evaluation must stay IEEE-exact on
+    every class of operand: random BIT patterns cover subnormals, huge values, inf, nan, 0."""
+    rng = np.random.default_rng(41)
+    a = rng.integers(0, 1 << 32, 1 << 21, dtype=np.uint32).view(np.float32)
+    b = rng.integers(0, 1 << 32, 1 << 21, dtype=np.uint32).view(np.float32)
+    with np.errstate(all="ignore"):
+        assert_bits_equal((gpu.array(a) / gpu.array(b)).get(), a / b, "div bits")
+        assert_bits_equal(np.sqrt(gpu.array(a)).get(), np.sqrt(a), "sqrt bits")
+        pos = np.abs(a)
+        got, want = np.log(gpu.array(pos)).get(), np.log(pos)
+        assert_close_to_numpy_or_truth(got[np.isfinite(want)], want[np.isfinite(want)], np.log,
+                                       (pos[np.isfinite(want)],), 2, "log bits")
+        assert np.array_equal(np.isnan(got), np.isnan(want)) and np.array_equal(np.isinf(got), np.isinf(want))
+        # moderate magnitudes (the fast path proper), many samples
+        c = rng.uniform(-1e3, 1e3, 1 << 22).astype(np.float32)
+        d = rng.uniform(1e-3, 1e3, 1 << 22).astype(np.float32)
+        assert_bits_equal((gpu.array(c) / gpu.array(d)).get(), c / d, "div moderate")
+        assert_bits_equal(np.sqrt(gpu.array(d)).get(), np.sqrt(d), "sqrt moderate")
+        assert_bits_equal((1.0 / gpu.array(d)).get(), (1.0 / d).astype(np.float32), "reciprocal")
 
 
 # ------------------------------------------------------------------ C2: Black-Scholes
@@ -303,7 +339,7 @@ def test_broadcast_where_and_mixed_ops(gpu):
     assert (z + 1).get().shape == (0, 5)
     assert float(np.sum(z).get()) == 0.0
     s = gpu.array(np.float64(3.0))
-    assert float((s * 2).get()) == 6.0
+    assert float((s * 2).get()[()]) == 6.0
 
 
 def test_matvec_gemm_and_dot_variants(gpu):
