@@ -216,8 +216,13 @@ def gen_flat(name, prog, in_class, out_dts, vec_ok, stream, reduce=None, unroll=
         params += [f"{A}* __restrict__ partials", "unsigned int* __restrict__ counter",
                    f"{ctype(res_dt)}* __restrict__ result", "const double post_scale"]
 
+    lockstep = lockstep_ok(prog, V) and os.environ.get("DR_LOCKSTEP", "1") != "0"
+    if lockstep:
+        two_tier = two_tier or has_lane_fast(prog)
     safe_body = emit_body(prog, fast=False)
     fast_body = emit_body(prog, fast=True) if two_tier else safe_body
+    if lockstep:
+        lock_body, lock_uniform = emit_body_lockstep(prog, in_class, V)
     src = []
     w = src.append
     if two_tier:
@@ -236,6 +241,7 @@ def gen_flat(name, prog, in_class, out_dts, vec_ok, stream, reduce=None, unroll=
             w(f"  res.o0 = ({A}){_operand_name(prog.roots[0])};")
         w("  return res;")
         w("}")
+    min_blocks = min_blocks or int(os.environ.get("DR_MINBLOCKS", 0)) or None
     lb = f"__launch_bounds__({threads}" + (f", {min_blocks})" if min_blocks else ")")
     w(f'extern "C" __global__ void {lb} {name}({", ".join(params)}) {{')
     for i, (a, c) in enumerate(zip(arrays, in_class)):
@@ -260,18 +266,37 @@ def gen_flat(name, prog, in_class, out_dts, vec_ok, stream, reduce=None, unroll=
         else:
             w(f"{p}val[e] = ({A}){_operand_name(prog.roots[0])};")
 
-    w(f"  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += {U} * stride) {{")
-    for i, (a, c) in enumerate(zip(arrays, in_class)):
-        if c == "c":
-            w(f"    Vec<{ctype(a.dtype)}, {V}> v{i}[{U}];")
-    w("#pragma unroll")
-    w(f"    for (int u = 0; u < {U}; ++u) {{")
-    w("      const i64 iu = i + u * stride;")
-    w("      const i64 ic = iu < nv ? iu : nv - 1;       // idle slots re-read a valid vector")
-    for i, (a, c) in enumerate(zip(arrays, in_class)):
-        if c == "c":
-            w(f"      v{i}[u] = dr_ld<{S}, {ctype(a.dtype)}, {V}>(in{i} + ic * {V});")
-    w("    }")
+    prefetch = U == 1 and body_weight(prog) >= 2 and os.environ.get("DR_PREFETCH", "0") != "0"
+    if prefetch:
+        # software pipelining: the loads of the NEXT vector are in flight while this one is
+        # evaluated (a heavy body with one vector per trip would otherwise expose DRAM latency)
+        w("  i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;")
+        for i, (a, c) in enumerate(zip(arrays, in_class)):
+            if c == "c":
+                w(f"  Vec<{ctype(a.dtype)}, {V}> v{i}[1], nx{i};")
+        w("  if (i < nv) {")
+        for i, (a, c) in enumerate(zip(arrays, in_class)):
+            if c == "c":
+                w(f"    v{i}[0] = dr_ld<{S}, {ctype(a.dtype)}, {V}>(in{i} + i * {V});")
+        w("  }")
+        w("  for (; i < nv; i += stride) {")
+        w("    const i64 inx = i + stride < nv ? i + stride : i;")
+        for i, (a, c) in enumerate(zip(arrays, in_class)):
+            if c == "c":
+                w(f"    nx{i} = dr_ld<{S}, {ctype(a.dtype)}, {V}>(in{i} + inx * {V});")
+    else:
+        w(f"  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += {U} * stride) {{")
+        for i, (a, c) in enumerate(zip(arrays, in_class)):
+            if c == "c":
+                w(f"    Vec<{ctype(a.dtype)}, {V}> v{i}[{U}];")
+        w("#pragma unroll")
+        w(f"    for (int u = 0; u < {U}; ++u) {{")
+        w("      const i64 iu = i + u * stride;")
+        w("      const i64 ic = iu < nv ? iu : nv - 1;       // idle slots re-read a valid vector")
+        for i, (a, c) in enumerate(zip(arrays, in_class)):
+            if c == "c":
+                w(f"      v{i}[u] = dr_ld<{S}, {ctype(a.dtype)}, {V}>(in{i} + ic * {V});")
+        w("    }")
     w("#pragma unroll")
     w(f"    for (int u = 0; u < {U}; ++u) {{")
     if reduce is None:
@@ -281,10 +306,21 @@ def gen_flat(name, prog, in_class, out_dts, vec_ok, stream, reduce=None, unroll=
         w(f"      {A} val[{V}];")
     if two_tier:
         w("      bool bad = false;")
-    w("#pragma unroll")
-    w(f"      for (int e = 0; e < {V}; ++e) {{")
-    element(fast_body, "        ", None)
-    w("      }")
+    if lockstep:
+        for line in lock_body:
+            w(f"      {line}")
+        w("#pragma unroll")
+        w(f"      for (int e = 0; e < {V}; ++e) {{")
+        for o, (r, dt) in enumerate(zip(prog.roots, out_dts) if reduce is None else []):
+            w(f"        r{o}.v[e] = {_lane_store(prog, r, dt, in_class, lock_uniform)};")
+        if reduce is not None:
+            w(f"        val[e] = ({A}){_lane_name(prog.roots[0], in_class, lock_uniform)};")
+        w("      }")
+    else:
+        w("#pragma unroll")
+        w(f"      for (int e = 0; e < {V}; ++e) {{")
+        element(fast_body, "        ", None)
+        w("      }")
     if two_tier:
         w("      if (bad) {                                 // rare: precise re-evaluation")
         w("#pragma unroll")
@@ -309,6 +345,10 @@ def gen_flat(name, prog, in_class, out_dts, vec_ok, stream, reduce=None, unroll=
         w(f"        for (int e = 0; e < {V}; ++e) acc[u] = {_RED[rop]}::op(acc[u], val[e]);")
         w("      }")
     w("    }")
+    if prefetch:
+        for i, (a, c) in enumerate(zip(arrays, in_class)):
+            if c == "c":
+                w(f"    v{i}[0] = nx{i};")
     w("  }")
     # scalar tail: the n - nv*V < V trailing elements, first threads of block 0, precise forms
     if V > 1:
@@ -329,6 +369,97 @@ def gen_flat(name, prog, in_class, out_dts, vec_ok, stream, reduce=None, unroll=
         _emit_reduce_finish(w, rop, acc_dt, res_dt, U)
     w("}")
     return "\n".join(src) + "\n"
+
+
+_PACKED = {"add": "dr_add4", "subtract": "dr_sub4", "multiply": "dr_mul4"}
+_LANE4_FAST = {"true_divide": "dr_div4_fast", "divide": "dr_div4_fast", "sqrt": "dr_sqrt4_fast",
+               "log": "dr_log4_f32", "exp": "dr_exp4_f32", "erf": "dr_erf4_fast"}
+if os.environ.get("DR_F64_EXPLOG"):          # previous generation: double-precision exp/log
+    _LANE4_FAST.update({"log": "dr_log4_fast", "exp": "dr_exp4_fast"})
+F32 = np.dtype(np.float32)
+if os.environ.get("DR_F32_NATIVE"):
+    _LANE4_FAST.update({"log": "dr_log4_native", "exp": "dr_exp4_native", "erf": "dr_erf4_native"})
+
+
+def lockstep_ok(prog, V):
+    """The 4-lane lockstep form applies to float32 vectors of four."""
+    return V == 4
+
+
+def has_lane_fast(prog):
+    return any(op in _LANE4_FAST and loop[0] == F32 for op, loop, _, _ in prog.instrs)
+
+
+def emit_body_lockstep(prog, in_class, V=4):
+    """Lane-array form of the fused body: every SSA value is `T tK[4]` (or a plain scalar when
+    it only depends on scalars / broadcast operands) and each instruction is applied to all
+    four lanes at once -- packed f32x2 for float32 + - *, the dr_*4_fast lane functions for
+    / sqrt log exp erf, an unrolled lane loop for everything else."""
+    lines = []
+    uniform = {}
+    packed_products = set()          # temps produced by a packed multiply
+
+    def is_uniform(r):
+        if r[0] == "s":
+            return True
+        if r[0] == "a":
+            return in_class[r[1]] == "b"
+        return uniform[r]
+
+    def arr(r):                      # array (or scalar) expression naming the operand
+        if r[0] == "a":
+            return f"x{r[1]}" if in_class[r[1]] == "b" else f"v{r[1]}[u].v"
+        return _operand_name(r)
+
+    def lane(r):
+        return arr(r) if is_uniform(r) else f"{arr(r)}[e]"
+
+    for k, (op, loop, out_dt, args) in enumerate(prog.instrs):
+        me = ("t", k)
+        dts = [prog.dtypes[r] for r in args]
+        T = ctype(out_dt)
+        if all(is_uniform(r) for r in args):
+            uniform[me] = True
+            lines.append(f"const {T} t{k} = {emit_expr(op, loop, out_dt, [arr(r) for r in args], dts)};")
+            continue
+        uniform[me] = False
+        lines.append(f"{T} t{k}[{V}];")
+        same = all(d == F32 for d in dts) and all(d == F32 for d in loop) and out_dt == F32
+        if same and op in ("add", "subtract") and V == 4 and any(r in packed_products for r in args):
+            # ptxas fuses mul.rn.f32x2 + add/sub.rn.f32x2 into FFMA2 even though both carry an
+            # explicit .rn (observed, CUDA 12.9; the scalar forms are never fused).  An add
+            # that consumes a packed product therefore stays scalar: a*b+c must round twice.
+            fn = "__fadd_rn" if op == "add" else "__fsub_rn"
+            lines.append(f"_Pragma(\"unroll\") for (int e = 0; e < {V}; ++e) "
+                         f"t{k}[e] = {fn}({lane(args[0])}, {lane(args[1])});")
+        elif same and op in _PACKED and V == 4:
+            lines.append(f"{_PACKED[op]}({arr(args[0])}, {arr(args[1])}, t{k});")
+            if op == "multiply":
+                packed_products.add(me)
+        elif same and op in _LANE4_FAST and V == 4:
+            lines.append(f"{_LANE4_FAST[op]}({', '.join(arr(r) for r in args)}, t{k}, bad);")
+        else:
+            expr = emit_expr(op, loop, out_dt, [lane(r) for r in args], dts)
+            lines.append(f"_Pragma(\"unroll\") for (int e = 0; e < {V}; ++e) t{k}[e] = {expr};")
+    return lines, uniform
+
+
+def _lane_name(ref, in_class, uniform):
+    if ref[0] == "s":
+        return _operand_name(ref)
+    if ref[0] == "a":
+        return f"x{ref[1]}" if in_class[ref[1]] == "b" else f"v{ref[1]}[u].v[e]"
+    return _operand_name(ref) if uniform[ref] else f"{_operand_name(ref)}[e]"
+
+
+def _lane_store(prog, ref, out_dt, in_class, uniform):
+    have = prog.dtypes[ref]
+    nm = _lane_name(ref, in_class, uniform)
+    if have == out_dt:
+        return nm
+    if np.dtype(out_dt).kind == "b":
+        return f"({nm} != 0)"
+    return f"(({ctype(out_dt)})({nm}))"
 
 
 def _store_expr(prog, ref, out_dt):

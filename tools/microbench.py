@@ -77,6 +77,30 @@ extern "C" __global__ void k_mix_packed(float* out, double a, double b, float c,
   for (int i = 0; i < 8; ++i) s += y[i].x + y[i].y;
   out[blockIdx.x * blockDim.x + threadIdx.x] = (float)s;
 }
+__constant__ double HC[12] = {1e-7, 2e-6, -3e-5, 2e-4, -8e-4, 2e-3, -3e-4, -2e-2, 0.1, 0.6, 1.1, 0.5};
+// Horner chains with constant-bank coefficients, LANES chains interleaved, plus per-trip
+// conversion f32->f64 at the start and f64->f32 at the end (the shape of dr_erf4_fast)
+template <int LANES> __device__ void horner_body(float* out, float seed) {
+  float x[LANES];
+  for (int l = 0; l < LANES; ++l) x[l] = seed + threadIdx.x * 1e-4f + l * 0.01f;
+  for (int it = 0; it < 256; ++it) {
+    double a[LANES], p[LANES];
+#pragma unroll
+    for (int l = 0; l < LANES; ++l) { a[l] = (double)x[l]; p[l] = HC[0]; }
+#pragma unroll
+    for (int i = 1; i < 12; ++i)
+#pragma unroll
+      for (int l = 0; l < LANES; ++l)
+        asm volatile("fma.rn.f64 %0, %1, %2, %3;" : "=d"(p[l]) : "d"(p[l]), "d"(a[l]), "d"(HC[i]));
+#pragma unroll
+    for (int l = 0; l < LANES; ++l) x[l] = (float)p[l];
+  }
+  float s = 0; for (int l = 0; l < LANES; ++l) s += x[l];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+extern "C" __global__ void k_horner1(float* out, float s) { horner_body<1>(out, s); }
+extern "C" __global__ void k_horner2(float* out, float s) { horner_body<2>(out, s); }
+extern "C" __global__ void k_horner4(float* out, float s) { horner_body<4>(out, s); }
 extern "C" __global__ void k_f2f(float* out, float a) {
   float x[8];
   for (int i = 0; i < 8; ++i) x[i] = threadIdx.x * 1e-3f + i;
@@ -134,6 +158,34 @@ def main():
     run("k_mix_scalar", a_f((1.0001, "f8"), (1e-4, "f8"), (1.0001, "f4"), (1e-4, "f4")), IT // 2 * 20, "4 DFMA + 16 FFMA  (ops=20/it)")
     run("k_mix_packed", a_f((1.0001, "f8"), (1e-4, "f8"), (1.0001, "f4"), (1e-4, "f4")), IT // 2 * 20, "4 DFMA + 8 FFMA2  (ops=20/it)")
     run("k_f2f", a_f((1.0, "f4"),), IT // 4 * 8 * 2, "F2F f32->f64->f32 (conv ops)")
+    # latency / occupancy study: limit resident warps with a small grid
+    def run_occ(name, args, ops_per_thread, label, blocks_per_sm, thr):
+        fn = C.c_uint64()
+        check(lib.drc_module_get_function(dev, mod, name.encode(), C.byref(fn)))
+        k = engine.Kernel(name, "", cubin, {})
+        k.funcs[dev] = fn.value
+        best = 1e9
+        for _ in range(3):
+            check(lib.drc_event_record(dev, 0, ev[0].value))
+            engine.launch(k, dev, 148 * blocks_per_sm, thr, args)
+            check(lib.drc_event_record(dev, 0, ev[1].value))
+            check(lib.drc_event_sync(dev, ev[1].value))
+            ms = C.c_float()
+            check(lib.drc_event_elapsed_ms(dev, ev[0].value, ev[1].value, C.byref(ms)))
+            best = min(best, ms.value)
+        total = ops_per_thread * 148 * blocks_per_sm * thr
+        print(f"{label:44s} {best:8.3f} ms  {total / (best * 1e-3) / 148 / 1.9e9:7.1f} ops/clk/SM")
+    for warps_per_sm in (4, 8, 16, 24, 32):
+        for ch in (1, 4):
+            run_occ(f"k_dfma{ch}", a_f((1.0001, "f8"), (1e-4, "f8")), IT * 8,
+                    f"DFMA {ch} chain(s), {warps_per_sm} warps/SM", 1, warps_per_sm * 32)
+    for warps_per_sm in (8, 16, 24, 32):
+        for lanes in (1, 2, 4):
+            run_occ(f"k_horner{lanes}", a_f((0.5, "f4"),), 256 * 11 * lanes,
+                    f"Horner(11 DFMA)+2 F2F, {lanes} lane(s), {warps_per_sm} warps/SM", 1, warps_per_sm * 32)
+    for warps_per_sm in (8, 16, 24, 32):
+        run_occ("k_mix_packed", a_f((1.0001, "f8"), (1e-4, "f8"), (1.0001, "f4"), (1e-4, "f4")),
+                IT // 2 * 20, f"4 DFMA + 8 FFMA2, {warps_per_sm} warps/SM", 1, warps_per_sm * 32)
 
 
 if __name__ == "__main__":
