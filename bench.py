@@ -124,6 +124,66 @@ def reference_arm(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------ other configs
+def bench_others(dr, wl, lib, check, dev, peak, reps=10):
+    """BASELINE.json configs 1, 3, 4, 5 at full size: device-resident inputs, CUDA events on the
+    launch stream, mean over `reps` after 2 warm-ups.  Reported for context next to the headline
+    (they are parity-test cases, not the bench line)."""
+    import ctypes as C
+    out = {}
+
+    def timed(fn, n_rep=reps, warm=2):
+        for _ in range(warm):
+            fn()
+        a, b = C.c_uint64(), C.c_uint64()
+        check(lib.drc_event_create(dev, C.byref(a)))
+        check(lib.drc_event_create(dev, C.byref(b)))
+        dr.synchronize()
+        check(lib.drc_event_record(dev, 0, a.value))
+        for _ in range(n_rep):
+            fn()
+        check(lib.drc_event_record(dev, 0, b.value))
+        check(lib.drc_event_sync(dev, b.value))
+        ms = C.c_float()
+        check(lib.drc_event_elapsed_ms(dev, a.value, b.value, C.byref(ms)))
+        return ms.value / n_rep
+
+    def entry(name, ms, units, unit, bytes_per_unit):
+        gbs = units * bytes_per_unit / (ms * 1e-3) / 1e9
+        out[name] = {"ms": ms, "value": units / (ms * 1e-3), "unit": unit, "achieved_GBs": gbs,
+                     "frac_of_measured_hbm": gbs / peak, "bytes_per_unit": bytes_per_unit}
+
+    # C1 axpy f64 N=2^24
+    n = 1 << 24
+    i = wl.make_inputs("axpy", n)
+    x, y = dr.array(i["x"]), dr.array(i["y"])
+    entry("axpy_f64_2^24", timed(lambda: wl.axpy(dr, i["a"], x, y).run(), 50), n, "elems/s", 24)
+    del x, y
+    # C3 fused reductions f64 N=2^30 (seeded 2^22 chunk tiled on the device)
+    n = 1 << 30
+    i = wl.make_inputs("l2", 1 << 22)
+    a = dr.tile(dr.array(i["a"]), n >> 22)
+    b = dr.tile(dr.array(i["b"]), n >> 22)
+    entry("l2_distance_f64_2^30", timed(lambda: wl.l2_distance(dr, a, b).run()), n, "elems/s", 16)
+    entry("dot_f64_2^30", timed(lambda: wl.dot(dr, a, b).run()), n, "elems/s", 16)
+    entry("norm_f64_2^30", timed(lambda: wl.norm(dr, a).run()), n, "elems/s", 8)
+    del a, b
+    # C4 heat 32768^2 f32, 100 steps
+    g = 32768
+    u = dr.tile(dr.array(wl.make_inputs("heat", 2048)["u"]), (g // 2048, g // 2048))
+    steps = 100
+    ms = timed(lambda: wl.heat(dr, u, steps), 1, 1)
+    entry("heat_f32_32768^2_x100", ms / steps, g * g, "cell-steps/s", 8)
+    del u
+    # C5 n-body N=65536 (all-pairs producer fused into the contraction)
+    nb = 65536
+    i = wl.make_inputs("nbody", nb)
+    pos, m = dr.array(i["pos"]), dr.array(i["m"])
+    ms = timed(lambda: wl.nbody_acc(dr, pos, m).run(), 2, 1)
+    out["nbody_f32_65536"] = {"ms": ms, "value": nb * nb / (ms * 1e-3), "unit": "pairs/s"}
+    return out
+
+
 # ------------------------------------------------------------------------------ GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -136,6 +196,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--others", action="store_true", help="also time configs 1, 3, 4, 5 (N=1)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -263,6 +324,10 @@ def main():
         return
 
     peak, peak_src = _peaks()
+    others = None
+    if args.others and world == 1:
+        hin = hout = None
+        others = bench_others(dr, wl, lib, check, dev, peak)
     achieved = BYTES_PER_OPTION * n / (kernel_ms * 1e-3) / 1e9
     cpu = None
     if not args.no_cpu:
@@ -286,7 +351,7 @@ def main():
                      "algorithmic_bytes_per_launch": BYTES_PER_OPTION * n,
                      "kernel_ms": kernel_ms},
         "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-        "clocks": clocks, "host_wall_s": host_s,
+        "clocks": clocks, "host_wall_s": host_s, "other_configs": others,
         "engine": {k: (round(v, 1) if isinstance(v, float) else v) for k, v in engine.stats.items()},
     }
     print(json.dumps(line), flush=True)

@@ -647,3 +647,137 @@ def gen_cols(name, prog, in_class, reduce, threads=256):
     w("  }")
     w("}")
     return "\n".join(src) + "\n"
+
+
+# --------------------------------------------------------------------------- stencil family
+def gen_stencil(name, prog, roles, out_dt, TW=128, TH=32, NS=3, threads=256):
+    """Shifted-view stencil over ONE 2-d base array, written to a fresh copy of the base
+    (ping-pong: Jacobi semantics without the reference's temporary + copy, delayarray.py:114-121).
+
+    roles[i] = ("tile", dy, dx)  operand i is the base array shifted by (dy, dx) relative to the
+                                 cell being written -> read from the TMA-staged shared tile
+             = ("b",)            broadcast scalar operand (one global load)
+             = ("g",)            another array over the target region -> coalesced global load
+    Persistent CTAs walk the tiles of the base; an NS-deep ring of (TH + halo) x (TW + halo)
+    boxes is filled by cp.async.bulk.tensor.2d + mbarrier so the load of tile t+NS-1 overlaps the
+    arithmetic of tile t.  Each thread produces 4 consecutive cells (one 128-bit store) per row
+    pass through the lockstep / packed-f32x2 body.  Cells of the base outside the assigned view
+    are copied through unchanged."""
+    arrays, scalars = prog.arrays, prog.scalars
+    T = ctype(out_dt)
+    V = 16 // np.dtype(out_dt).itemsize
+    tiles = [r for r in roles if r[0] == "tile"]
+    hu = max(0, -min(r[1] for r in tiles))
+    hd = max(0, max(r[1] for r in tiles))
+    hl = max(0, -min(r[2] for r in tiles))
+    hr = max(0, max(r[2] for r in tiles))
+    hl_pad = -(-hl // V) * V                       # keep the tile's own columns 16-byte aligned
+    BW = hl_pad + TW + (-(-hr // V) * V)
+    BH = hu + TH + hd
+    assert BW <= 256 and BH <= 256
+    stage_bytes = BW * BH * np.dtype(out_dt).itemsize
+    stage_bytes_al = -(-stage_bytes // 128) * 128
+    cols_per_row = TW // V                          # threads along x
+    rows_per_pass = threads // cols_per_row
+    in_class = tuple("b" if r[0] == "b" else "c" for r in roles)
+    lock_body, lock_uniform = emit_body_lockstep(prog, in_class, V) if V == 4 else (None, None)
+    scalar_body = emit_body(prog, fast=False)
+    src = []
+    w = src.append
+    w(f"struct Geo_{name} {{ int rows, cols, r0, c0, h, w, tiles_x, ntiles; i64 pitch_elems; "
+      f"i64 gs_row[{max(len(arrays), 1)}]; i64 gs_col[{max(len(arrays), 1)}]; }};")
+    params = [f"const __grid_constant__ DrTensorMap tmap", f"const Geo_{name} g",
+              f"const {T}* __restrict__ base", f"{T}* __restrict__ out"]
+    for i, a in enumerate(arrays):
+        params.append(f"const char* __restrict__ in{i}")
+    for j, (_, dt) in enumerate(scalars):
+        params.append(f"const {ctype(dt)} s{j}")
+    w(f'extern "C" __global__ void __launch_bounds__({threads}) {name}({", ".join(params)}) {{')
+    w("  extern __shared__ __align__(128) unsigned char dr_smem[];")
+    w(f"  __shared__ __align__(8) unsigned long long bar[{NS}];")
+    w("  const int tid = threadIdx.x;")
+    w(f"  if (tid == 0) {{ for (int s = 0; s < {NS}; ++s) dr_mbar_init(&bar[s], 1); dr_fence_barrier_init(); }}")
+    w("  __syncthreads();")
+    for i, (a, r) in enumerate(zip(arrays, roles)):
+        if r[0] == "b":
+            w(f"  const {ctype(a.dtype)} x{i} = *reinterpret_cast<const {ctype(a.dtype)}*>(in{i});")
+    w(f"  const int tx = tid % {cols_per_row}, ty = tid / {cols_per_row};")
+    w("  auto issue = [&](int tile, int stage) {")
+    w("    if (tile < g.ntiles) {")
+    w(f"      const int by = tile / g.tiles_x, bx = tile - by * g.tiles_x;")
+    w(f"      dr_mbar_expect_tx(&bar[stage], {stage_bytes});")
+    w(f"      dr_tma_load_2d(dr_smem + stage * {stage_bytes_al}, &tmap, bx * {TW} - {hl_pad}, by * {TH} - {hu}, &bar[stage]);")
+    w("    }")
+    w("  };")
+    w(f"  if (tid == 0) {{ for (int k = 0; k < {NS - 1}; ++k) issue(blockIdx.x + k * gridDim.x, k); }}")
+    w("  int it = 0;")
+    w("  for (int tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x, ++it) {")
+    w(f"    const int stage = it % {NS};")
+    w(f"    if (tid == 0) issue(tile + {NS - 1} * gridDim.x, (it + {NS - 1}) % {NS});")
+    w(f"    dr_mbar_wait(&bar[stage], (it / {NS}) & 1);")
+    w(f"    const {T}* sm = reinterpret_cast<const {T}*>(dr_smem + stage * {stage_bytes_al});")
+    w("    const int by = tile / g.tiles_x, bx = tile - by * g.tiles_x;")
+    w(f"    const int gx = bx * {TW} + tx * {V};")
+    w("#pragma unroll")
+    w(f"    for (int pass = 0; pass < {TH // rows_per_pass}; ++pass) {{")
+    w(f"      const int ly = pass * {rows_per_pass} + ty, gy = by * {TH} + ly;")
+    w("      if (gy < g.rows && gx < g.cols) {")
+    w("        constexpr int u = 0;")
+    # gather operands
+    for i, (a, r) in enumerate(zip(arrays, roles)):
+        A = ctype(a.dtype)
+        if r[0] == "tile":
+            dy, dx = r[1], r[2]
+            w(f"        Vec<{A}, {V}> v{i}[1];")
+            row = f"(ly + {hu + dy}) * {BW} + {hl_pad + dx} + tx * {V}"
+            if (hl_pad + dx) % V == 0:
+                w(f"        v{i}[0] = *reinterpret_cast<const Vec<{A}, {V}>*>(sm + {row});")
+            else:
+                w(f"#pragma unroll\n        for (int e = 0; e < {V}; ++e) v{i}[0].v[e] = sm[{row} + e];")
+        elif r[0] == "g":
+            w(f"        Vec<{A}, {V}> v{i}[1];")
+            w(f"#pragma unroll\n        for (int e = 0; e < {V}; ++e) {{")
+            w(f"          const int yy = min(max(gy - g.r0, 0), g.h - 1), xx = min(max(gx + e - g.c0, 0), g.w - 1);")
+            w(f"          v{i}[0].v[e] = *reinterpret_cast<const {A}*>(in{i} + yy * g.gs_row[{i}] + xx * g.gs_col[{i}]);")
+            w("        }")
+    w(f"        Vec<{T}, {V}> keep = *reinterpret_cast<const Vec<{T}, {V}>*>(sm + (ly + {hu}) * {BW} + {hl_pad} + tx * {V});")
+    w(f"        Vec<{T}, {V}> r0;")
+    if lock_body is not None:
+        w("        bool bad = false;")
+        for line in lock_body:
+            w(f"        {line}")
+        w(f"#pragma unroll\n        for (int e = 0; e < {V}; ++e) r0.v[e] = {_lane_store(prog, prog.roots[0], out_dt, in_class, lock_uniform)};")
+        if has_lane_fast(prog):
+            w("        if (bad) {")
+            w(f"#pragma unroll\n          for (int e = 0; e < {V}; ++e) {{")
+            for i, (a, r) in enumerate(zip(arrays, roles)):
+                if r[0] != "b":
+                    w(f"            const {ctype(a.dtype)} x{i} = v{i}[0].v[e];")
+            for line in scalar_body:
+                w(f"            {line}")
+            w(f"            r0.v[e] = {_store_expr(prog, prog.roots[0], out_dt)};")
+            w("          }")
+            w("        }")
+    else:
+        w(f"#pragma unroll\n        for (int e = 0; e < {V}; ++e) {{")
+        for i, (a, r) in enumerate(zip(arrays, roles)):
+            if r[0] != "b":
+                w(f"          const {ctype(a.dtype)} x{i} = v{i}[0].v[e];")
+        for line in scalar_body:
+            w(f"          {line}")
+        w(f"          r0.v[e] = {_store_expr(prog, prog.roots[0], out_dt)};")
+        w("        }")
+    w("        const bool row_in = gy >= g.r0 && gy < g.r0 + g.h;")
+    w(f"#pragma unroll\n        for (int e = 0; e < {V}; ++e) {{")
+    w("          const int x = gx + e;")
+    w("          if (!(row_in && x >= g.c0 && x < g.c0 + g.w)) r0.v[e] = keep.v[e];")
+    w("        }")
+    w(f"        dr_st<true, {T}, {V}>(out + (i64)gy * g.pitch_elems + gx, r0);")
+    w("      }")
+    w("    }")
+    w("    __syncthreads();")
+    w("  }")
+    w("}")
+    meta = dict(TW=TW, TH=TH, NS=NS, BW=BW, BH=BH, hl_pad=hl_pad, hu=hu, smem=NS * stage_bytes_al,
+                threads=threads)
+    return "\n".join(src) + "\n", meta

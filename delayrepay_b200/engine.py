@@ -590,6 +590,9 @@ def assign(target, value):
                 inplace = True
             else:
                 hazard = True
+    if hazard and _try_stencil(prog, target):
+        target.buf.version += 1
+        return
     if hazard:
         tmp = DeviceArray.empty(target.shape, target.dtype, target.dev)
         run_program(prog, [tmp])
@@ -599,6 +602,100 @@ def assign(target, value):
     else:
         run_program(prog, [target], inplace=inplace)
     target.buf.version += 1
+
+
+_TMA_DTYPE = {"float32": 0, "float64": 1, "int32": 2, "int64": 3, "uint8": 4}
+
+
+def _try_stencil(prog, target):
+    """Shifted-view self-assignment on a 2-d base array -> TMA-staged stencil kernel writing a
+    fresh copy of the base, then the two allocations are swapped (ping-pong).  Returns False
+    when the pattern does not apply (the caller falls back to temporary + copy)."""
+    if os.environ.get("DR_NO_STENCIL") or target.ndim != 2 or target.dtype.name not in ("float32", "float64"):
+        return False
+    item = target.dtype.itemsize
+    V = 16 // item
+    buf = target.buf
+    pitch = target.strides[0]
+    if target.strides[1] != item or pitch % 16 or pitch <= 0 or buf.ptr % 16:
+        return False
+    cols = pitch // item
+    if cols % V:
+        return False
+    rows = buf.nbytes // pitch
+    if rows * pitch != buf.nbytes or rows >= (1 << 31) or cols >= (1 << 31):
+        return False                       # the buffer is not exactly one rows x cols matrix
+    r0, rem = divmod(target.offset, pitch)
+    c0 = rem // item
+    h, w = target.shape
+    if c0 + w > cols or r0 + h > rows or 2 * h * w < rows * cols:
+        return False
+    roles = []
+    for arr in prog.arrays:
+        if arr.buf is buf:
+            if arr.dtype != target.dtype or arr.shape != target.shape or arr.strides != target.strides:
+                return False
+            ar, rem = divmod(arr.offset, pitch)
+            ac = rem // item
+            if ac + w > cols:
+                return False
+            roles.append(("tile", ar - r0, ac - c0))
+        elif all(s == 0 for s in planner.broadcast_strides(arr, target.shape)):
+            roles.append(("b",))
+        else:
+            roles.append(("g",))
+    tiles = [r for r in roles if r[0] == "tile"]
+    if not tiles or max(abs(r[1]) for r in tiles) > 8 or max(abs(r[2]) for r in tiles) > 8:
+        return False
+    dev = target.dev
+    st = dev_state(dev)
+    key = ("stencil", prog.key(), tuple(roles), target.dtype.str)
+    meta_box = {}
+
+    def gen(name):
+        src, meta = codegen.gen_stencil(name, prog, roles, target.dtype)
+        meta_box.update(meta)
+        return src
+    kern = get_kernel(key, gen, meta_box)
+    if not kern.meta:
+        kern.meta.update(codegen.gen_stencil("x", prog, roles, target.dtype)[1])
+    m = kern.meta
+    out = DeviceBuffer(buf.nbytes, dev) if dev >= 0 else DeviceBuffer(buf.nbytes)
+    tiles_x, tiles_y = -(-cols // m["TW"]), -(-rows // m["TH"])
+    a = Args()
+    tmap = (C.c_uint8 * 128)()
+    if dev >= 0:
+        dims = (C.c_uint64 * 2)(cols, rows)
+        strides = (C.c_uint64 * 1)(pitch)
+        box = (C.c_uint32 * 2)(m["BW"], m["BH"])
+        check(lib.drc_tensormap_encode(dev, tmap, _TMA_DTYPE[target.dtype.name], 2, buf.ptr, dims,
+                                       strides, box, 0, 2))
+    a.raw(bytes(tmap), 64)
+    n_ops = max(len(prog.arrays), 1)
+    gs_row, gs_col = [0] * n_ops, [0] * n_ops
+    for i, (arr, role) in enumerate(zip(prog.arrays, roles)):
+        if role[0] == "g":
+            bst = planner.broadcast_strides(arr, target.shape)
+            gs_row[i], gs_col[i] = bst
+    geo = np.asarray([rows, cols, r0, c0, h, w, tiles_x, tiles_x * tiles_y], dtype=np.int32).tobytes() \
+        + np.asarray([cols] + gs_row + gs_col, dtype=np.int64).tobytes()
+    a.raw(geo, 8)
+    a.ptr(buf.ptr)
+    a.ptr(out.ptr)
+    for arr in prog.arrays:
+        a.ptr(arr.ptr)
+    for val, dt in prog.scalars:
+        a.scalar(val, dt)
+    if dev >= 0 and not kern.meta.get("smem_set"):
+        check(lib.drc_func_set_max_dynamic_smem(dev, kern.func(dev), m["smem"]))
+        kern.meta["smem_set"] = True
+    per_sm = max(1, min(8, (st.max_smem - 1024) // (m["smem"] + 1024)))
+    if dev >= 0:
+        per_sm = min(per_sm, kern.blocks_per_sm(dev, m["threads"], m["smem"]))
+    grid = min(tiles_x * tiles_y, st.sm_count * per_sm)
+    launch(kern, dev, grid, m["threads"], a, smem=m["smem"])
+    buf.swap_storage(out)              # `out` now owns the old allocation and frees it (stream-ordered)
+    return True
 
 
 def _scalar_program(node):
