@@ -180,7 +180,7 @@ def _identity(op, dt):
 
 # --------------------------------------------------------------------------- flat family
 def gen_flat(name, prog, in_class, out_dts, vec_ok, stream, reduce=None, unroll=None,
-             threads=256, min_blocks=None):
+             threads=256, min_blocks=None, meta=None):
     """Contiguous 1-d kernel.  ``reduce`` = None or (op, acc np.dtype, result np.dtype, post).
 
     One copy of the fused body per vector lane (plus one scalar-tail copy): each thread loads
@@ -241,7 +241,8 @@ def gen_flat(name, prog, in_class, out_dts, vec_ok, stream, reduce=None, unroll=
             w(f"  res.o0 = ({A}){_operand_name(prog.roots[0])};")
         w("  return res;")
         w("}")
-    min_blocks = min_blocks or int(os.environ.get("DR_MINBLOCKS", 0)) or None
+    min_blocks = min_blocks or int(os.environ.get("DR_MINBLOCKS", 0)) or (
+        4 if (lockstep and body_weight(prog) >= 2) else None)     # measured best on B200 (C2)
     lb = f"__launch_bounds__({threads}" + (f", {min_blocks})" if min_blocks else ")")
     w(f'extern "C" __global__ void {lb} {name}({", ".join(params)}) {{')
     for i, (a, c) in enumerate(zip(arrays, in_class)):
@@ -250,6 +251,9 @@ def gen_flat(name, prog, in_class, out_dts, vec_ok, stream, reduce=None, unroll=
     if reduce is not None:
         w(f"  {A} acc[{U}];")
         w(f"#pragma unroll\n  for (int u = 0; u < {U}; ++u) acc[u] = {_identity(rop, acc_dt)};")
+    if lockstep and uses_erf_table(prog):
+        w("  __shared__ float2 dr_erf_tab[DR_ERF_TAB_PAIRS];")
+        w("  dr_erf_tab_stage(dr_erf_tab);")
     w(f"  const i64 nv = n / {V};")
     w("  const i64 stride = (i64)gridDim.x * blockDim.x;")
 
@@ -266,8 +270,46 @@ def gen_flat(name, prog, in_class, out_dts, vec_ok, stream, reduce=None, unroll=
         else:
             w(f"{p}val[e] = ({A}){_operand_name(prog.roots[0])};")
 
-    prefetch = U == 1 and body_weight(prog) >= 2 and os.environ.get("DR_PREFETCH", "0") != "0"
-    if prefetch:
+    c_inputs = [(i, a) for i, (a, c) in enumerate(zip(arrays, in_class)) if c == "c"]
+    staged = (U == 1 and V > 1 and body_weight(prog) >= 2 and c_inputs
+              and all(a.dtype.itemsize * V == 16 for _, a in c_inputs)
+              and os.environ.get("DR_STAGED", "1") != "0")
+    NS = int(os.environ.get("DR_STAGES", 3))
+    prefetch = (not staged) and U == 1 and body_weight(prog) >= 2 \
+        and os.environ.get("DR_PREFETCH", "0") != "0"
+    if meta is not None:
+        meta["smem"] = NS * len(c_inputs) * threads * 16 if staged else 0
+    if staged:
+        # operands arrive through an NS-deep shared-memory ring filled by 1-d TMA bulk copies
+        # (one elected thread issues them, an mbarrier per stage counts the bytes): the loads of
+        # tile t+NS-1 are in flight while tile t is evaluated, and no register is held for them
+        nin = len(c_inputs)
+        w("  extern __shared__ __align__(128) unsigned char dr_smem[];")
+        w(f"  __shared__ __align__(8) unsigned long long dr_bar[{NS}];")
+        w(f"  if (threadIdx.x == 0) {{ for (int s = 0; s < {NS}; ++s) dr_mbar_init(&dr_bar[s], 1); dr_fence_barrier_init(); }}")
+        w("  __syncthreads();")
+        w(f"  const i64 ntiles = (nv + {threads - 1}) / {threads};")
+        w("  auto dr_issue = [&](i64 tile, int stage) {")
+        w("    if (tile < ntiles) {")
+        w(f"      const i64 v0 = tile * {threads};")
+        w(f"      const unsigned bytes = (unsigned)(nv - v0 < {threads} ? nv - v0 : {threads}) * 16u;")
+        w(f"      dr_mbar_expect_tx(&dr_bar[stage], bytes * {nin}u);")
+        for slot, (i, a) in enumerate(c_inputs):
+            w(f"      dr_bulk_load(dr_smem + (stage * {nin} + {slot}) * {threads * 16}, in{i} + v0 * {V}, bytes, &dr_bar[stage]);")
+        w("    }")
+        w("  };")
+        w(f"  if (threadIdx.x == 0) {{ for (int k = 0; k < {NS - 1}; ++k) dr_issue(blockIdx.x + (i64)k * gridDim.x, k); }}")
+        w("  int dr_it = 0;")
+        w("  for (i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++dr_it) {")
+        w(f"    const int stage = dr_it % {NS};")
+        w(f"    if (threadIdx.x == 0) dr_issue(tile + (i64){NS - 1} * gridDim.x, (dr_it + {NS - 1}) % {NS});")
+        w(f"    dr_mbar_wait(&dr_bar[stage], (dr_it / {NS}) & 1);")
+        w(f"    const i64 i = tile * {threads} + threadIdx.x;")
+        w("    if (i < nv) {")
+        for slot, (i, a) in enumerate(c_inputs):
+            w(f"    Vec<{ctype(a.dtype)}, {V}> v{i}[1];")
+            w(f"    v{i}[0] = *reinterpret_cast<const Vec<{ctype(a.dtype)}, {V}>*>(dr_smem + (stage * {nin} + {slot}) * {threads * 16} + threadIdx.x * 16);")
+    elif prefetch:
         # software pipelining: the loads of the NEXT vector are in flight while this one is
         # evaluated (a heavy body with one vector per trip would otherwise expose DRAM latency)
         w("  i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;")
@@ -349,6 +391,9 @@ def gen_flat(name, prog, in_class, out_dts, vec_ok, stream, reduce=None, unroll=
         for i, (a, c) in enumerate(zip(arrays, in_class)):
             if c == "c":
                 w(f"    v{i}[0] = nx{i};")
+    if staged:
+        w("    }")
+        w("    __syncthreads();          // everyone is done with this stage before it is refilled")
     w("  }")
     # scalar tail: the n - nv*V < V trailing elements, first threads of block 0, precise forms
     if V > 1:
@@ -373,9 +418,14 @@ def gen_flat(name, prog, in_class, out_dts, vec_ok, stream, reduce=None, unroll=
 
 _PACKED = {"add": "dr_add4", "subtract": "dr_sub4", "multiply": "dr_mul4"}
 _LANE4_FAST = {"true_divide": "dr_div4_fast", "divide": "dr_div4_fast", "sqrt": "dr_sqrt4_fast",
-               "log": "dr_log4_f32", "exp": "dr_exp4_f32", "erf": "dr_erf4_fast"}
-if os.environ.get("DR_F64_EXPLOG"):          # previous generation: double-precision exp/log
-    _LANE4_FAST.update({"log": "dr_log4_fast", "exp": "dr_exp4_fast"})
+               "log": "dr_log4_f32", "exp": "dr_exp4_f32", "erf": "dr_erf4_tab"}
+if os.environ.get("DR_F64_EXPLOG"):          # previous generation: double-precision exp/log/erf
+    _LANE4_FAST.update({"log": "dr_log4_fast", "exp": "dr_exp4_fast", "erf": "dr_erf4_fast"})
+
+
+def uses_erf_table(prog):
+    return _LANE4_FAST["erf"] == "dr_erf4_tab" and any(
+        op == "erf" and loop[0] == np.float32 for op, loop, _, _ in prog.instrs)
 F32 = np.dtype(np.float32)
 if os.environ.get("DR_F32_NATIVE"):
     _LANE4_FAST.update({"log": "dr_log4_native", "exp": "dr_exp4_native", "erf": "dr_erf4_native"})
@@ -437,7 +487,8 @@ def emit_body_lockstep(prog, in_class, V=4):
             if op == "multiply":
                 packed_products.add(me)
         elif same and op in _LANE4_FAST and V == 4:
-            lines.append(f"{_LANE4_FAST[op]}({', '.join(arr(r) for r in args)}, t{k}, bad);")
+            extra = ", dr_erf_tab" if _LANE4_FAST[op] == "dr_erf4_tab" else ""
+            lines.append(f"{_LANE4_FAST[op]}({', '.join(arr(r) for r in args)}, t{k}, bad{extra});")
         else:
             expr = emit_expr(op, loop, out_dt, [lane(r) for r in args], dts)
             lines.append(f"_Pragma(\"unroll\") for (int e = 0; e < {V}; ++e) t{k}[e] = {expr};")
@@ -701,6 +752,9 @@ def gen_stencil(name, prog, roles, out_dt, TW=128, TH=32, NS=3, threads=256):
     for i, (a, r) in enumerate(zip(arrays, roles)):
         if r[0] == "b":
             w(f"  const {ctype(a.dtype)} x{i} = *reinterpret_cast<const {ctype(a.dtype)}*>(in{i});")
+    if lock_body is not None and uses_erf_table(prog):
+        w("  __shared__ float2 dr_erf_tab[DR_ERF_TAB_PAIRS];")
+        w("  dr_erf_tab_stage(dr_erf_tab);")
     w(f"  const int tx = tid % {cols_per_row}, ty = tid / {cols_per_row};")
     w("  auto issue = [&](int tile, int stage) {")
     w("    if (tile < g.ntiles) {")

@@ -220,9 +220,9 @@ def launch(kernel, dev, grid, block, args, smem=0, stream=0, cluster=1):
     stats["launches"] += 1
 
 
-def _grid_for(kernel, dev, threads, work_items):
+def _grid_for(kernel, dev, threads, work_items, smem=0):
     st = dev_state(dev)
-    cap = st.sm_count * (kernel.blocks_per_sm(dev, threads) if dev >= 0 else 8)
+    cap = st.sm_count * (kernel.blocks_per_sm(dev, threads, smem) if dev >= 0 else 8)
     need = max(1, -(-work_items // threads))
     return min(need, cap)
 
@@ -256,8 +256,10 @@ def run_program(prog, outs, reduce=None, inplace=False):
         key = ("flat", prog.key(), lay.in_class, tuple(d.str for d in out_dts), lay.vec_ok,
                stream_hint, red_key, inplace)
         gen_reduce = None if reduce is None else (reduce[0], reduce[1], reduce[2], None)
+        meta = {}
         kern = get_kernel(key, lambda name: codegen.gen_flat(
-            name, prog, lay.in_class, out_dts, lay.vec_ok, stream_hint, gen_reduce))
+            name, prog, lay.in_class, out_dts, lay.vec_ok, stream_hint, gen_reduce, meta=meta), meta)
+        smem = kern.meta.get("smem", 0)
         a = Args()
         a.i64(lay.total)
         for arr in prog.arrays:
@@ -269,8 +271,12 @@ def run_program(prog, outs, reduce=None, inplace=False):
         widest = max([x.dtype.itemsize for x, c in zip(prog.arrays, lay.in_class) if c == "c"]
                      + [d.itemsize for d in out_dts] + [1])
         vec = max(1, 16 // widest) if lay.vec_ok else 1
-        grid = _grid_for(kern, dev, 256, -(-lay.total // vec))
+        if smem > 40 * 1024 and dev >= 0 and not kern.meta.get("smem_set"):
+            check(lib.drc_func_set_max_dynamic_smem(dev, kern.func(dev), smem))
+            kern.meta["smem_set"] = True
+        grid = _grid_for(kern, dev, 256, -(-lay.total // vec), smem)
     else:
+        smem = 0
         wide = lay.total >= (1 << 32) or any(
             abs(s) * n >= (1 << 62) for stv in lay.in_strides for s, n in zip(stv, lay.shape))
         key = ("nd", prog.key(), len(lay.shape), lay.in_class, tuple(d.str for d in out_dts),
@@ -296,7 +302,7 @@ def run_program(prog, outs, reduce=None, inplace=False):
         a.ptr(st.counter_ptr)
         a.ptr(reduce[4].ptr)
         a.f64(reduce[3])
-    launch(kern, dev, grid, 256, a)
+    launch(kern, dev, grid, 256, a, smem=smem)
 
 
 def evaluate_nodes(nodes, outs=None, inplace=False):

@@ -97,7 +97,7 @@ def test_all_workloads_generate_and_compile(dry):
     dr.evaluate(call, put)
     assert len(dry) == n0 + 1, "call and put must share ONE fused kernel"
     kern = dry[-1][0]
-    assert kern.source.count("dr_erf(") >= 2 and "dr_ld<" in kern.source
+    assert "dr_erf4_tab(" in kern.source and "dr_bulk_load(" in kern.source   # staged + lockstep
     i = wl.make_inputs("l2", 4096)
     a, b = dr.array(i["a"]), dr.array(i["b"])
     n0 = len(dry)

@@ -94,3 +94,75 @@ if __name__ == "__main__":
     e = ulp_err(log_f32(x), np.log(x.astype(LD)))
     i = e.argmax()
     print(f"log f32: max {e.max():.4f} ulp at {x[i]!r}, mean {e.mean():.4f}   p = [{fmt(LOG_P)}]")
+
+
+# ------------------------------------------------------------------ erf: table-driven, float32 only
+# a = |x|.  a < 1/8: a*c0h + a*(c0l + s P(s)), s = a^2.  1/8 <= a < 4: 40 intervals (8 per binade,
+# index from the float's exponent + top 3 mantissa bits), centre c_j, d = a - c_j (exact):
+#   erf(a) = C0h_j + (C0l_j + d (C1_j + d (C2_j + d (C3_j + d (C4_j + d C5_j)))))
+from scipy.special import erf as _erf
+C0 = 2 / np.sqrt(np.pi)
+ERF_C0H = f32(C0)
+ERF_C0L = f32(C0 - float(ERF_C0H))
+
+
+def _small_target(s):        # (erf(a)/a - c0) / s  with s = a^2
+    a = np.sqrt(s.astype(np.float64))
+    a = np.where(a == 0, 1e-6, a)
+    return ((_erf(a) / a - C0) / (a * a)).astype(LD)
+
+# Taylor: erf(a)/a = c0 (1 - s/3 + s^2/10 - s^3/42 ...); fit P(s) = -c0/3 + c0 s/10 - ...
+def _small_series(s):
+    s = s.astype(LD)
+    return LD(C0) * (-LD(1) / 3 + s / 10 - s * s / 42 + s * s * s / 216)
+ERF_SMALL = cheb_fit(_small_series, 0.0, 1.0 / 64, 2).astype(f32)
+
+
+def erf_table():
+    rows = []
+    for j in range(40):
+        e, m = divmod(j, 8)
+        lo = 2.0 ** (e - 3) * (1 + m / 8)
+        hi = 2.0 ** (e - 3) * (1 + (m + 1) / 8)
+        c = 0.5 * (lo + hi)
+        fit = cheb_fit(lambda d, c=c: _erf((c + d).astype(np.float64)).astype(LD),
+                       lo - c, hi - c, 5)
+        c0h = f32(fit[0])
+        c0l = f32(fit[0] - float(c0h))
+        rows.append([c0h, c0l] + [f32(v) for v in fit[1:]] + [f32(0)])
+    return np.array(rows, dtype=f32)            # (40, 8): C0h C0l C1 C2 C3 C4 C5 pad
+ERF_TAB = erf_table()
+
+
+def erf_f32(x):
+    a = np.minimum(np.abs(x), f32(3.9999998))
+    bits = a.view(np.int32)
+    j = np.clip((bits >> 20) - 0x3e0, 0, 39)
+    c = ((bits & np.int32(-1048576)) | np.int32(0x00080000)).view(f32)
+    d = a - c
+    T = ERF_TAB[j]
+    p = T[:, 6]
+    for k in (5, 4, 3, 2):
+        p = fma(p, d, T[:, k])
+    t = fma(p, d, T[:, 1])
+    big = T[:, 0] + t
+    s = a * a
+    q = f32(ERF_SMALL[2])
+    q = fma(q, s, f32(ERF_SMALL[1]))
+    q = fma(q, s, f32(ERF_SMALL[0]))
+    q = fma(q, s, ERF_C0L)
+    small = fma(a, ERF_C0H, a * q)
+    return np.copysign(np.where(a < f32(0.125), small, big), x)
+
+
+if __name__ == "__main__":
+    rng = np.random.default_rng(3)
+    x = np.concatenate([rng.uniform(-4.5, 4.5, 1 << 22), rng.uniform(-0.13, 0.13, 1 << 21),
+                        np.exp(rng.uniform(-40, 1.5, 1 << 21)) * rng.choice([-1, 1], 1 << 21),
+                        np.linspace(0.1249, 4.0, 1 << 21)]).astype(f32)
+    truth = _erf(x.astype(np.float64)).astype(LD)
+    e = ulp_err(erf_f32(x), truth)
+    i = e.argmax()
+    print(f"erf f32 (table): max {e.max():.4f} ulp at {x[i]!r}, mean {e.mean():.4f}")
+    ok = np.abs(x) < 0.125
+    print("   small branch max", e[ok].max(), " table branch max", e[~ok].max())
