@@ -64,7 +64,7 @@ def body_weight(prog):
     return sum(1 for op, _, _, _ in prog.instrs if op in _HEAVY)
 
 
-def emit_expr(op, loop, out_dt, args, arg_dts, fast=False):
+def emit_expr(op, loop, out_dt, args, arg_dts, fast=False, relaxed=False):
     """C expression for one SSA instruction; ``args`` are C expressions of dtype arg_dts.
     ``fast``: use the branch-free flag-raising float32 forms (see prelude, dr_*_fast)."""
     cast_args = []
@@ -113,6 +113,8 @@ def emit_expr(op, loop, out_dt, args, arg_dts, fast=False):
     if op == "invert":
         return f"(!{a[0]})" if k == "b" else f"(({O})(~{a[0]}))"
     if op == "power":
+        if relaxed and loop[0] == np.float32:
+            return f"dr_pow_relaxed({a[0]}, {a[1]})"
         return f"dr_pow({a[0]}, {a[1]})" if k == "f" else f"dr_ipow<{T}>({a[0]}, {a[1]})"
     if op in ("deg2rad", "radians"):
         return f"({a[0]} * (({T})0.017453292519943295))"
@@ -135,14 +137,16 @@ def _operand_name(ref):
     return {"a": "x", "s": "s", "t": "t"}[ref[0]] + str(ref[1])
 
 
-def emit_body(prog, fast=False):
-    """The fused scalar body: `const T tK = expr;` lines over x<i> (arrays), s<j> (scalars)."""
+def emit_body(prog, fast=False, relaxed=False):
+    """The fused scalar body: `const T tK = expr;` lines over x<i> (arrays), s<j> (scalars).
+    ``relaxed``: inside a contraction, where only the reduced result is observable (rtol bar),
+    float32 pow with a uniform exponent may take its reciprocal-square-root form."""
     lines = []
     for k, (op, loop, out_dt, args) in enumerate(prog.instrs):
         exprs = [_operand_name(r) for r in args]
         dts = [prog.dtypes[r] for r in args]
         lines.append(f"const {ctype(out_dt)} t{k} = "
-                     f"{emit_expr(op, loop, out_dt, exprs, dts, fast)};")
+                     f"{emit_expr(op, loop, out_dt, exprs, dts, fast, relaxed)};")
     return lines
 
 
@@ -835,3 +839,71 @@ def gen_stencil(name, prog, roles, out_dt, TW=128, TH=32, NS=3, threads=256):
     meta = dict(TW=TW, TH=TH, NS=NS, BW=BW, BH=BH, hl_pad=hl_pad, hu=hu, smem=NS * stage_bytes_al,
                 threads=threads)
     return "\n".join(src) + "\n", meta
+
+
+# --------------------------------------------------------------------------- skinny contraction
+def gen_mm_skinny(name, prog, roles, t_dt, n_out, threads=256, tile_k=256):
+    """out[i, 0:n_out] (+)= sum_k A(i, k) * B[k, 0:n_out] where A is a fused elementwise program
+    whose array operands each vary along rows only ('r'), along k only ('c') or not at all ('b')
+    -- the all-pairs pattern x[None, :] - x[:, None] ... of the n-body workload.  One thread per
+    output row, B and the k-varying operands staged through shared memory per k-tile (broadcast
+    reads), accumulation in registers; grid.y splits K, each split writes its own partial block
+    (deterministic: the partials are summed by a second fused kernel, no atomics).  B's last
+    column may be a virtual column of ones (row sum of A folded into the same pass)."""
+    arrays, scalars = prog.arrays, prog.scalars
+    T = ctype(t_dt)
+    n_ops = max(len(arrays), 1)
+    src = []
+    w = src.append
+    w(f"struct Geo_{name} {{ i64 M, K, kchunk; i64 sr[{n_ops}]; i64 sc[{n_ops}]; i64 b_rs, b_cs; int n_real; }};")
+    params = [f"const Geo_{name} g"]
+    for i, a in enumerate(arrays):
+        params.append(f"const char* __restrict__ in{i}")
+    for j, (_, dt) in enumerate(scalars):
+        params.append(f"const {ctype(dt)} s{j}")
+    params += ["const char* __restrict__ B", f"{T}* __restrict__ partial"]
+    body = emit_body(prog, fast=False, relaxed=True)
+    w(f'extern "C" __global__ void __launch_bounds__({threads}) {name}({", ".join(params)}) {{')
+    cols = [i for i, r in enumerate(roles) if r == "c"]
+    for i in cols:
+        w(f"  __shared__ {ctype(arrays[i].dtype)} sh{i}[{tile_k}];")
+    w(f"  __shared__ {T} shB[{tile_k}][{n_out}];")
+    w("  const int tid = threadIdx.x;")
+    w(f"  const i64 row = (i64)blockIdx.x * {threads} + tid;")
+    w("  const i64 rr = row < g.M ? row : g.M - 1;")
+    for i, (a, r) in enumerate(zip(arrays, roles)):
+        A = ctype(a.dtype)
+        if r == "b":
+            w(f"  const {A} x{i} = *reinterpret_cast<const {A}*>(in{i});")
+        elif r == "r":
+            w(f"  const {A} x{i} = *reinterpret_cast<const {A}*>(in{i} + rr * g.sr[{i}]);")
+    w(f"  {T} acc[{n_out}];")
+    w(f"#pragma unroll\n  for (int n = 0; n < {n_out}; ++n) acc[n] = ({T})0;")
+    w("  const i64 k0 = (i64)blockIdx.y * g.kchunk;")
+    w("  const i64 k1 = k0 + g.kchunk < g.K ? k0 + g.kchunk : g.K;")
+    w(f"  for (i64 kt = k0; kt < k1; kt += {tile_k}) {{")
+    w("    const i64 kk = kt + tid < k1 ? kt + tid : k1 - 1;")
+    for i in cols:
+        A = ctype(arrays[i].dtype)
+        w(f"    sh{i}[tid] = *reinterpret_cast<const {A}*>(in{i} + kk * g.sc[{i}]);")
+    w(f"#pragma unroll\n    for (int n = 0; n < {n_out}; ++n)")
+    w(f"      shB[tid][n] = n < g.n_real ? *reinterpret_cast<const {T}*>(B + kk * g.b_rs + n * g.b_cs) : ({T})1;")
+    w("    __syncthreads();")
+    w(f"    const int lim = (int)(k1 - kt < {tile_k} ? k1 - kt : {tile_k});")
+    w("#pragma unroll 4")
+    w("    for (int j = 0; j < lim; ++j) {")
+    for i in cols:
+        w(f"      const {ctype(arrays[i].dtype)} x{i} = sh{i}[j];")
+    for line in body:
+        w(f"      {line}")
+    root = _store_expr(prog, prog.roots[0], t_dt)
+    w(f"      const {T} a_ik = {root};")
+    w(f"#pragma unroll\n      for (int n = 0; n < {n_out}; ++n) acc[n] = fma(a_ik, shB[j][n], acc[n]);")
+    w("    }")
+    w("    __syncthreads();")
+    w("  }")
+    w("  if (row < g.M) {")
+    w(f"#pragma unroll\n    for (int n = 0; n < {n_out}; ++n) partial[((i64)blockIdx.y * g.M + row) * {n_out} + n] = acc[n];")
+    w("  }")
+    w("}")
+    return "\n".join(src) + "\n"

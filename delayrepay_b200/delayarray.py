@@ -386,7 +386,14 @@ class _Elementwise(NumpyEx, Funcable):
         self.op = func.__name__
         self.children = list(kids)
         self.loop, self.dtype = resolve_loop(func, kids)
-        self.shape = np.broadcast_shapes(*[k.shape for k in kids])
+        shp = kids[0].shape
+        for k in kids[1:]:                     # fast paths: equal shapes / scalar operands
+            if k.shape != shp:
+                shp = k.shape if shp == () else (shp if k.shape == () else None)
+                if shp is None:
+                    shp = tuple(np.broadcast_shapes(*[kk.shape for kk in kids]))
+                    break
+        self.shape = shp
 
     @classmethod
     def _memo_key(cls, func, *kids):
@@ -466,6 +473,16 @@ class CastEx(NumpyEx):
         return f"cast{self._count}"
 
 
+def _register_consumer(producer, consumer):
+    """Cut nodes announce themselves to their lazy producer so that two cuts over the same
+    producer (W @ pos and W.sum(1) in the n-body workload) can share one pass."""
+    if producer.kind == "ewise":
+        cons = producer.__dict__.get("_consumers")
+        if cons is None:
+            cons = producer._consumers = weakref.WeakSet()
+        cons.add(consumer)
+
+
 class ReduceEx(NumpyEx, Funcable):
     """func.reduce(arg, axis)  [delayarray.py:272-283]; fused with its elementwise producer.
     ``post`` = "mean" divides by the reduced count in the kernel epilogue."""
@@ -478,6 +495,7 @@ class ReduceEx(NumpyEx, Funcable):
         self.op = _REDUCE_UFUNCS[func.__name__]
         self.children = [arg]
         self.post = post
+        _register_consumer(arg, self)
         nd = arg.ndim
         if axis is None:
             axes = tuple(range(nd))
@@ -518,6 +536,7 @@ class _Contraction(NumpyEx, Funcable):
         self.func = np.dot
         self.arg1, self.arg2 = arg1, arg2
         self.children = [arg1, arg2]
+        _register_consumer(arg1, self)
         self.dtype = np.result_type(arg1.dtype, arg2.dtype)
         if self.dtype.kind not in "f":
             self.dtype = np.result_type(self.dtype)      # integer dot keeps the integer type

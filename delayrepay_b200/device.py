@@ -98,7 +98,9 @@ class DeviceArray:
         if isinstance(shape, (int, np.integer)):
             shape = (int(shape),)
         dtype = np.dtype(dtype)
-        n = int(np.prod(shape, dtype=np.int64)) if len(shape) else 1
+        n = 1
+        for s in shape:
+            n *= int(s)
         return cls(DeviceBuffer(n * dtype.itemsize, dev), shape, dtype)
 
     @classmethod

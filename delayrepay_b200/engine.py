@@ -366,8 +366,17 @@ def _group_strides(arr_strides, shape, lo, hi):
 
 
 def _run_reduce(node):
-    from .delayarray import NPArray, ReduceEx
+    from .delayarray import MMEx, NPArray, ReduceEx
     child = node.children[0]
+    if node.op == "sum" and node.axes == (1,) and child.ndim == 2 and not node.keepdims:
+        # a pending A @ B over the same lazy producer A: one pass computes both (the row sum
+        # rides along as a virtual column of ones), see _try_mm_skinny
+        for cons in list(getattr(child, "_consumers", ())):
+            if isinstance(cons, MMEx) and cons.arg1 is child and cons.__dict__.get("array") is None \
+                    and cons.shape[1] <= 6 and child.kind == "ewise":
+                cons._force()
+                if node.__dict__.get("array") is not None:
+                    return node.array
     op = node.op
     res_dt = node.dtype
     nd = child.ndim
@@ -524,6 +533,9 @@ def _run_matmul(node):
         for buf in p.leaf_bufs:
             if all(buf is not x for x in prog.leaf_bufs):
                 prog.leaf_bufs.append(buf)
+    skinny = _try_mm_skinny(node, pa, m, k, n, res_dt)
+    if skinny is not None:
+        return skinny
     prod = ("t", len(prog.instrs))
     prog.instrs.append(("multiply", (res_dt, res_dt), res_dt, (remap["A"], remap["B"])))
     prog.dtypes[prod] = res_dt
@@ -539,6 +551,70 @@ def _run_matmul(node):
     _launch_axis_reduce(prog, triples, m, k, n, "sum", codegen.acc_dtype("sum", res_dt), res_dt,
                         1.0, result, dev)
     return result
+
+
+def _try_mm_skinny(node, pa, m, k, n, res_dt, with_rowsum=None):
+    """A(M,K) @ B(K,n<=7) with a fused all-pairs producer -> gen_mm_skinny.  If a live, not yet
+    evaluated ReduceEx(sum, A, axis=1) shares the same producer it is folded in as a virtual
+    column of ones and receives its result from this pass too."""
+    from .delayarray import NPArray, ReduceEx
+    if os.environ.get("DR_NO_SKINNY") or n > 7 or res_dt.kind != "f" or m < 512 or k < 512:
+        return None
+    a_node, b_node = node.arg1, node.arg2
+    roles = []
+    for arr in pa.arrays:
+        sm, sk = planner.broadcast_strides(arr, (m, k))
+        if sm == 0 and sk == 0:
+            roles.append("b")
+        elif sk == 0:
+            roles.append("r")
+        elif sm == 0:
+            roles.append("c")
+        else:
+            return None
+    if not pa.instrs:
+        return None
+    b_dev = b_node._force()
+    if b_dev.dtype != res_dt:
+        b_dev = b_dev.astype(res_dt)
+    rowsum = None
+    for cons in list(getattr(a_node, "_consumers", ())):
+        if isinstance(cons, ReduceEx) and cons.op == "sum" and cons.axes == (1,) and not cons.keepdims \
+                and cons.post is None and cons.dtype == res_dt and cons.__dict__.get("array") is None:
+            rowsum = cons
+            break
+    n_out = n + (1 if rowsum is not None else 0)
+    dev = b_dev.dev
+    st = dev_state(dev)
+    ksplit = max(1, min(64, -(-k // 2048)))
+    kchunk = -(-k // ksplit)
+    kchunk = -(-kchunk // 256) * 256
+    ksplit = -(-k // kchunk)
+    key = ("mm_skinny", pa.key(), tuple(roles), res_dt.str, n_out)
+    kern = get_kernel(key, lambda name: codegen.gen_mm_skinny(name, pa, roles, res_dt, n_out))
+    partial = DeviceArray.empty((ksplit, m, n_out), res_dt, dev if dev >= 0 else None)
+    a = Args()
+    n_ops = max(len(pa.arrays), 1)
+    sr, sc = [0] * n_ops, [0] * n_ops
+    for i, arr in enumerate(pa.arrays):
+        sr[i], sc[i] = planner.broadcast_strides(arr, (m, k))
+    geo = np.asarray([m, k, kchunk] + sr + sc + [b_dev.strides[0], b_dev.strides[1]],
+                     dtype=np.int64).tobytes() + np.asarray([n, 0], dtype=np.int32).tobytes()
+    a.raw(geo, 8)
+    for arr in pa.arrays:
+        a.ptr(arr.ptr)
+    for val, dt in pa.scalars:
+        a.scalar(val, dt)
+    a.ptr(b_dev.ptr)
+    a.ptr(partial.ptr)
+    launch(kern, dev, (-(-m // 256), ksplit, 1), 256, a)
+    total = ReduceEx(np.add, NPArray(partial), 0, False)._force()        # (m, n_out), fixed order
+    node._stamp = _stamp_of(pa)
+    if rowsum is not None:
+        rowsum.array = total[:, n].copy()
+        rowsum._stamp = _stamp_of(pa)
+        return total[:, :n].copy()
+    return total
 
 
 # --------------------------------------------------------------------------- assignment / copies

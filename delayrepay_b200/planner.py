@@ -226,6 +226,21 @@ class Layout:
 def resolve_layout(prog, outs):
     """Pick the kernel family for program ``prog`` writing into DeviceArrays ``outs``."""
     shape = prog.shape
+    # fast path: every operand is a C-contiguous array of exactly the iteration shape
+    if len(shape) >= 1 and all(a.shape == shape and a.is_contiguous for a in prog.arrays) \
+            and all(o.shape == shape and o.is_contiguous for o in outs):
+        lay = Layout()
+        total = 1
+        for n in shape:
+            total *= n
+        lay.shape, lay.total = (total,), total
+        lay.in_strides = [(a.dtype.itemsize,) for a in prog.arrays]
+        lay.out_strides = [(o.dtype.itemsize,) for o in outs]
+        lay.family = "flat"
+        lay.in_class = ("c",) * len(prog.arrays)
+        lay.vec_ok = all(a.ptr % 16 == 0 for a in prog.arrays) and all(o.ptr % 16 == 0 for o in outs)
+        if total > 1 or not prog.arrays:
+            return lay
     ins = [broadcast_strides(a, shape) for a in prog.arrays]
     out_st = [broadcast_strides(o, shape) for o in outs]
     cshape, csts = collapse(shape, ins + out_st)
