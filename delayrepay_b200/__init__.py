@@ -10,6 +10,7 @@ from .delayarray import (DelayArray, NPArray, Scalar, BinaryNumpyEx, UnaryFuncEx
 from .device import (DeviceArray, set_device, current_device, synchronize,  # noqa: F401
                      pinned_empty)
 from . import random, fft                   # noqa: F401
+from .stream import map_chunks              # noqa: F401
 
 pi = backend.backend.np.pi
 __version__ = "0.1.0"
