@@ -338,6 +338,11 @@ def main():
     if args.others and world == 1:
         hin = hout = None
         others = bench_others(dr, wl, lib, check, dev, peak)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath) and args.log2n == 30:
+        with open(tpath) as f:
+            traffic = json.load(f).get("black_scholes_f32_call_put", {}).get("dram_bytes_per_launch")
     achieved = BYTES_PER_OPTION * n / (kernel_ms * 1e-3) / 1e9
     cpu = None
     if not args.no_cpu:
@@ -357,7 +362,7 @@ def main():
                    "parallelism": f"option axis sharded over {world} rank(s), no collective"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "frac_of_nominal_8000": achieved / 8000.0,
-                     "traffic": None, "peak_source": peak_src,
+                     "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": BYTES_PER_OPTION * n,
                      "kernel_ms": kernel_ms},
         "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),

@@ -705,7 +705,7 @@ def gen_cols(name, prog, in_class, reduce, threads=256):
 
 
 # --------------------------------------------------------------------------- stencil family
-def gen_stencil(name, prog, roles, out_dt, TW=128, TH=32, NS=3, threads=256):
+def gen_stencil(name, prog, roles, out_dt, TW=248, TH=32, NS=4, threads=496):
     """Shifted-view stencil over ONE 2-d base array, written to a fresh copy of the base
     (ping-pong: Jacobi semantics without the reference's temporary + copy, delayarray.py:114-121).
 
@@ -718,6 +718,10 @@ def gen_stencil(name, prog, roles, out_dt, TW=128, TH=32, NS=3, threads=256):
     arithmetic of tile t.  Each thread produces 4 consecutive cells (one 128-bit store) per row
     pass through the lockstep / packed-f32x2 body.  Cells of the base outside the assigned view
     are copied through unchanged."""
+    TW = int(os.environ.get("DR_ST_TW", TW))
+    TH = int(os.environ.get("DR_ST_TH", TH))
+    NS = int(os.environ.get("DR_ST_NS", NS))
+    threads = int(os.environ.get("DR_ST_THREADS", threads))
     arrays, scalars = prog.arrays, prog.scalars
     T = ctype(out_dt)
     V = 16 // np.dtype(out_dt).itemsize
@@ -781,24 +785,39 @@ def gen_stencil(name, prog, roles, out_dt, TW=128, TH=32, NS=3, threads=256):
     w(f"      const int ly = pass * {rows_per_pass} + ty, gy = by * {TH} + ly;")
     w("      if (gy < g.rows && gx < g.cols) {")
     w("        constexpr int u = 0;")
-    # gather operands
+    # gather operands: ONE aligned 128-bit shared load per distinct row offset dy; horizontally
+    # shifted views reuse that vector and fetch only the |dx| cells that fall outside it
+    # (scalar loads) -- 3 LDS.128 + 2 LDS.32 per 4 cells for the 5-point stencil instead of 11
+    row_vec = {}
+    for r in roles:
+        if r[0] == "tile" and r[1] not in row_vec:
+            dy = r[1]
+            nm = f"row{'m' if dy < 0 else 'p'}{abs(dy)}"
+            row_vec[dy] = nm
+            w(f"        const Vec<{T}, {V}> {nm} = *reinterpret_cast<const Vec<{T}, {V}>*>"
+              f"(sm + (ly + {hu + dy}) * {BW} + {hl_pad} + tx * {V});")
     for i, (a, r) in enumerate(zip(arrays, roles)):
         A = ctype(a.dtype)
         if r[0] == "tile":
             dy, dx = r[1], r[2]
             w(f"        Vec<{A}, {V}> v{i}[1];")
-            row = f"(ly + {hu + dy}) * {BW} + {hl_pad + dx} + tx * {V}"
-            if (hl_pad + dx) % V == 0:
-                w(f"        v{i}[0] = *reinterpret_cast<const Vec<{A}, {V}>*>(sm + {row});")
-            else:
-                w(f"#pragma unroll\n        for (int e = 0; e < {V}; ++e) v{i}[0].v[e] = sm[{row} + e];")
+            base = f"(ly + {hu + dy}) * {BW} + {hl_pad} + tx * {V}"
+            for e in range(V):
+                src_e = e + dx
+                if 0 <= src_e < V:
+                    w(f"        v{i}[0].v[{e}] = {row_vec[dy]}.v[{src_e}];")
+                else:
+                    w(f"        v{i}[0].v[{e}] = sm[{base} + {src_e}];")
         elif r[0] == "g":
             w(f"        Vec<{A}, {V}> v{i}[1];")
             w(f"#pragma unroll\n        for (int e = 0; e < {V}; ++e) {{")
             w(f"          const int yy = min(max(gy - g.r0, 0), g.h - 1), xx = min(max(gx + e - g.c0, 0), g.w - 1);")
             w(f"          v{i}[0].v[e] = *reinterpret_cast<const {A}*>(in{i} + yy * g.gs_row[{i}] + xx * g.gs_col[{i}]);")
             w("        }")
-    w(f"        Vec<{T}, {V}> keep = *reinterpret_cast<const Vec<{T}, {V}>*>(sm + (ly + {hu}) * {BW} + {hl_pad} + tx * {V});")
+    if 0 not in row_vec:
+        w(f"        const Vec<{T}, {V}> rowp0 = *reinterpret_cast<const Vec<{T}, {V}>*>"
+          f"(sm + (ly + {hu}) * {BW} + {hl_pad} + tx * {V});")
+    w(f"        const Vec<{T}, {V}> keep = rowp0;")
     w(f"        Vec<{T}, {V}> r0;")
     if lock_body is not None:
         w("        bool bad = false;")

@@ -62,7 +62,10 @@ _kernels = {}
 
 
 def kernel_name(key):
-    return "dr_" + hashlib.sha256(repr(key).encode()).hexdigest()[:20]
+    """dr_<family>_<structural hash>: the family (flat, nd, rows, cols, stencil, mm_skinny) is
+    readable in profiler launch lists."""
+    family = key[0] if isinstance(key, tuple) and isinstance(key[0], str) else "k"
+    return f"dr_{family}_" + hashlib.sha256(repr(key).encode()).hexdigest()[:16]
 
 
 def compile_source(name, body_source):
