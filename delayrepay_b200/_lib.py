@@ -82,6 +82,7 @@ _SIGS = {
     "drc_nccl_allgather": ([u64, i32, i32, u64, u64, sz], i32),
     "drc_nccl_group_start": ([], i32),
     "drc_nccl_group_end": ([], i32),
+    "drc_fft_c2c_1d": ([i32, i32, u64, u64, i32, i32, i32, i32], i32),
 }
 EXPORTS = tuple(_SIGS)
 

@@ -658,4 +658,59 @@ int drc_nccl_group_end(void) {
   return 0;
 }
 
+// ---------------------------------------------------------------- cuFFT
+namespace {
+typedef int cufftHandle_t;
+typedef int (*fn_cufftPlan1d)(cufftHandle_t*, int, int, int);
+typedef int (*fn_cufftSetStream)(cufftHandle_t, void*);
+typedef int (*fn_cufftExec)(cufftHandle_t, void*, void*, int);
+typedef int (*fn_cufftDestroy)(cufftHandle_t);
+void* g_libcufft = nullptr;
+fn_cufftPlan1d p_cufftPlan1d = nullptr;
+fn_cufftSetStream p_cufftSetStream = nullptr;
+fn_cufftExec p_cufftExecC2C = nullptr, p_cufftExecZ2Z = nullptr;
+struct FftPlan { int dev, n, batch, is_double; cufftHandle_t h; };
+std::vector<FftPlan> g_plans;
+
+int load_cufft() {
+  if (g_libcufft) return 0;
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_libcufft) return 0;
+  void* h = dlopen("libcufft.so.11", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libcufft.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) return fail("libcufft not found: %s", dlerror());
+  p_cufftPlan1d = (fn_cufftPlan1d)dlsym(h, "cufftPlan1d");
+  p_cufftSetStream = (fn_cufftSetStream)dlsym(h, "cufftSetStream");
+  p_cufftExecC2C = (fn_cufftExec)dlsym(h, "cufftExecC2C");
+  p_cufftExecZ2Z = (fn_cufftExec)dlsym(h, "cufftExecZ2Z");
+  if (!p_cufftPlan1d || !p_cufftSetStream || !p_cufftExecC2C || !p_cufftExecZ2Z)
+    return fail("libcufft lacks a required symbol");
+  g_libcufft = h;
+  return 0;
+}
+}  // namespace
+
+int drc_fft_c2c_1d(int dev, int stream, uint64_t in, uint64_t out, int n, int batch,
+                   int is_double, int inverse) {
+  if (int e = load_cufft()) return e;
+  USE(dev);
+  STREAM(dev, stream, s);
+  cufftHandle_t h = -1;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (auto& p : g_plans)
+      if (p.dev == dev && p.n == n && p.batch == batch && p.is_double == is_double) h = p.h;
+    if (h < 0) {
+      int r = p_cufftPlan1d(&h, n, is_double ? 0x69 : 0x29, batch);     // CUFFT_Z2Z : CUFFT_C2C
+      if (r != 0) return fail("cufftPlan1d(n=%d, batch=%d) failed: %d", n, batch, r);
+      g_plans.push_back({dev, n, batch, is_double, h});
+    }
+  }
+  int r = p_cufftSetStream(h, (void*)s);
+  if (r != 0) return fail("cufftSetStream failed: %d", r);
+  r = (is_double ? p_cufftExecZ2Z : p_cufftExecC2C)(h, (void*)in, (void*)out, inverse ? 1 : -1);
+  if (r != 0) return fail("cufftExec failed: %d", r);
+  return 0;
+}
+
 }  // extern "C"

@@ -599,7 +599,7 @@ class NPArray(NumpyEx):
         super().__init__()
         if not isinstance(array, (DeviceArray, np.ndarray)):
             array = np.asarray(array)
-        if array.dtype.kind not in "biuf":
+        if array.dtype.kind not in "biufc":      # complex: storage only (fft results)
             raise TypeError(f"dtype {array.dtype} is not supported on the device")
         self.array = array
         self.shape = tuple(array.shape)

@@ -792,8 +792,14 @@ def _scalar_program(node):
 
 
 def materialize_view(arr):
-    """Contiguous copy of a (possibly strided) DeviceArray."""
+    """Contiguous copy of a (possibly strided) DeviceArray.  Complex data (fft results) is moved
+    as (re, im) pairs of its component type."""
     from .delayarray import NPArray
+    if arr.dtype.kind == "c":
+        part = np.dtype(np.float32 if arr.dtype == np.complex64 else np.float64)
+        pairs = DeviceArray(arr.buf, arr.shape + (2,), part, arr.strides + (part.itemsize,), arr.offset)
+        flat = materialize_view(pairs)
+        return DeviceArray(flat.buf, arr.shape, arr.dtype, None, flat.offset)
     outs, _ = evaluate_nodes([NPArray(arr)])
     return outs[0]
 
@@ -805,7 +811,8 @@ def cast_array(arr, dtype):
 
 
 def cumsum(arr, axis=None):
-    raise NotImplementedError("cumsum: device scan kernel not implemented yet")
+    from . import extras
+    return extras.cumsum(arr, axis)
 
 
 def synchronize(dev=None):

@@ -122,6 +122,13 @@ int drc_nccl_allgather(uint64_t comm, int dev, int stream, uint64_t sendbuf, uin
 int drc_nccl_group_start(void);
 int drc_nccl_group_end(void);
 
+/* ---- FFT: cuFFT behind the C ABI -------------------------------------------------------
+ * Replaces `cupy.fft.fft` (reference fft.py:12).  Batched 1-d complex-to-complex transform of
+ * `batch` contiguous rows of length n (in place when in == out); plans are cached per
+ * (device, n, batch, precision).  libcufft is resolved at first use. */
+int drc_fft_c2c_1d(int dev, int stream, uint64_t in, uint64_t out, int n, int batch,
+                   int is_double, int inverse);
+
 #ifdef __cplusplus
 }
 #endif

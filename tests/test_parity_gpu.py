@@ -387,3 +387,60 @@ def test_map_chunks_streamed_equals_eager(gpu):
     gpu.evaluate(call, put)
     assert_bits_equal(hout[0], call.get(), "streamed call")
     assert_bits_equal(hout[1], put.get(), "streamed put")
+
+
+def test_cumsum(gpu):
+    rng = np.random.default_rng(43)
+    xi = rng.integers(-100, 100, 1_000_003)
+    assert_bits_equal(np.cumsum(gpu.array(xi)).get(), np.cumsum(xi), "int cumsum 1-d (3-phase)")
+    xf = rng.standard_normal(300_007)
+    np.testing.assert_allclose(np.cumsum(gpu.array(xf)).get(), np.cumsum(xf), rtol=1e-12, atol=1e-9)
+    m = rng.standard_normal((37, 53, 11)).astype(np.float32)
+    for axis in (0, 1, 2, None):
+        np.testing.assert_allclose(np.cumsum(gpu.array(m), axis=axis).get(), np.cumsum(m, axis=axis),
+                                   rtol=1e-5, atol=1e-4)
+    assert_bits_equal(np.cumsum(gpu.array(np.ones(10, np.int8))).get(), np.cumsum(np.ones(10, np.int8)), "int8 promotes")
+    lazy = np.cumsum(gpu.array(xf) * 2.0 + 1.0)
+    np.testing.assert_allclose(lazy.get(), np.cumsum(xf * 2.0 + 1.0), rtol=1e-12, atol=1e-9)
+
+
+def test_device_random_statistics(gpu):
+    """Philox on the device: statistical parity only (different generator from NumPy's)."""
+    gpu.random.seed(1234)
+    u = gpu.random.rand(1 << 20).get()
+    assert u.dtype == np.float64 and 0.0 <= u.min() and u.max() < 1.0
+    assert abs(u.mean() - 0.5) < 2e-3 and abs(u.var() - 1 / 12) < 1e-3
+    g = gpu.random.randn(1 << 20).get()
+    assert abs(g.mean()) < 5e-3 and abs(g.std() - 1.0) < 5e-3 and abs((g ** 3).mean()) < 2e-2
+    i = gpu.random.randint(3, 11, (1000, 257)).get()
+    assert i.shape == (1000, 257) and i.min() == 3 and i.max() == 10
+    counts = np.bincount(i.ravel() - 3, minlength=8) / i.size
+    assert np.all(np.abs(counts - 0.125) < 5e-3)
+    gpu.random.seed(1234)
+    assert_bits_equal(gpu.random.rand(1 << 20).get(), u, "seed reproducibility")
+    assert not np.array_equal(gpu.random.rand(1 << 20).get(), u)      # the stream advances
+    # histogram uniformity (chi-square, 64 bins)
+    h = np.histogram(u, bins=64, range=(0, 1))[0]
+    chi2 = ((h - u.size / 64) ** 2 / (u.size / 64)).sum()
+    assert chi2 < 130, chi2
+    assert gpu.random.rand(4, 3).shape == (4, 3) and gpu.random.random((2, 2)).shape == (2, 2)
+
+
+def test_fft_matches_numpy(gpu):
+    rng = np.random.default_rng(47)
+    x = rng.standard_normal(4096)
+    got = gpu.fft.fft(gpu.array(x)).get()
+    want = np.fft.fft(x)
+    assert got.dtype == np.complex128
+    np.testing.assert_allclose(got, want, rtol=1e-10, atol=1e-9)
+    m = rng.standard_normal((7, 1000)).astype(np.float32)
+    got = gpu.fft.fft(gpu.array(m)).get()
+    assert got.dtype == np.complex64
+    np.testing.assert_allclose(got, np.fft.fft(m), rtol=1e-4, atol=1e-2)
+    np.testing.assert_allclose(gpu.fft.fft(gpu.array(m), axis=0).get(), np.fft.fft(m, axis=0), rtol=1e-4, atol=1e-3)
+    np.testing.assert_allclose(gpu.fft.fft(gpu.array(x), n=1024).get(), np.fft.fft(x, n=1024), rtol=1e-10, atol=1e-9)
+    np.testing.assert_allclose(gpu.fft.fft(gpu.array(x), n=5000).get(), np.fft.fft(x, n=5000), rtol=1e-10, atol=1e-9)
+    back = gpu.fft.ifft(gpu.fft.fft(gpu.array(x))).get()
+    np.testing.assert_allclose(back.real, x, rtol=1e-10, atol=1e-10)
+    lazy = gpu.fft.fft(gpu.array(x) * 2.0)            # forces the lazy operand, like the reference
+    np.testing.assert_allclose(lazy.get(), np.fft.fft(x * 2.0), rtol=1e-10, atol=1e-9)
