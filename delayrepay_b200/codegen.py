@@ -83,6 +83,8 @@ def emit_expr(op, loop, out_dt, args, arg_dts, fast=False, relaxed=False):
     O = ctype(out_dt)
     if op == "cast":
         return f"({a[0]} != 0)" if out_dt.kind == "b" else f"(({O})({a[0]}))"
+    if op == "tf32_hi":          # nearest TF32-representable value (10 explicit mantissa bits)
+        return f"__uint_as_float((__float_as_uint({a[0]}) + 0x1000u) & 0xffffe000u)"
     if op == "where":
         return f"({a[0]} ? {a[1]} : {a[2]})"
     if k == "b" and op in ("add", "maximum", "bitwise_or", "logical_or"):

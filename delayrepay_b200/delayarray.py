@@ -483,6 +483,30 @@ def _register_consumer(producer, consumer):
         cons.add(consumer)
 
 
+class RawOp(NumpyEx):
+    """Engine-internal unary elementwise op that has no NumPy ufunc (e.g. "tf32_hi": keep the
+    TF32-representable part of a float32).  Never created by user code."""
+
+    kind = "ewise"
+
+    def __init__(self, op, arg):
+        super().__init__()
+        self.op = op
+        self.func = None
+        self.children = [arg]
+        self.loop = (arg.dtype,)
+        self.dtype = arg.dtype
+        self.shape = arg.shape
+
+    @classmethod
+    def _memo_key(cls, op, arg):
+        return (cls.__name__, op, _kid_key(arg))
+
+    @property
+    def name(self):
+        return f"raw{self._count}"
+
+
 class ReduceEx(NumpyEx, Funcable):
     """func.reduce(arg, axis)  [delayarray.py:272-283]; fused with its elementwise producer.
     ``post`` = "mean" divides by the reduced count in the kernel epilogue."""

@@ -539,6 +539,10 @@ def _run_matmul(node):
     skinny = _try_mm_skinny(node, pa, m, k, n, res_dt)
     if skinny is not None:
         return skinny
+    if res_dt == np.float32 and min(m, n) >= 128 and k >= 64 and not os.environ.get("DR_NO_TCGEN05"):
+        from . import gemm
+        node._stamp = _stamp_of(pa) + _stamp_of(pb)
+        return gemm.matmul_tf32x3(a, b)
     prod = ("t", len(prog.instrs))
     prog.instrs.append(("multiply", (res_dt, res_dt), res_dt, (remap["A"], remap["B"])))
     prog.dtypes[prod] = res_dt
@@ -692,6 +696,22 @@ def assign(target, value):
 _TMA_DTYPE = {"float32": 0, "float64": 1, "int32": 2, "int64": 3, "uint8": 4}
 
 
+def encode_tensormap(dev, dtype_name, gptr, dims, strides_bytes, box, swizzle=0, l2promo=2):
+    """cuTensorMapEncodeTiled through the C ABI; returns the 128 descriptor bytes.  The driver
+    wants the descriptor 64-byte aligned, so it is built inside an over-allocated buffer."""
+    raw = (C.c_uint8 * 256)()
+    base = C.addressof(raw)
+    off = (-base) % 64
+    rank = len(dims)
+    if dev >= 0:
+        d = (C.c_uint64 * rank)(*dims)
+        st = (C.c_uint64 * max(rank - 1, 1))(*(list(strides_bytes) or [0]))
+        bx = (C.c_uint32 * rank)(*box)
+        check(lib.drc_tensormap_encode(dev, C.c_void_p(base + off), _TMA_DTYPE[dtype_name], rank, gptr,
+                                       d, st, bx, swizzle, l2promo))
+    return bytes(raw[off:off + 128])
+
+
 def _try_stencil(prog, target):
     """Shifted-view self-assignment on a 2-d base array -> TMA-staged stencil kernel writing a
     fresh copy of the base, then the two allocations are swapped (ping-pong).  Returns False
@@ -748,14 +768,8 @@ def _try_stencil(prog, target):
     out = DeviceBuffer(buf.nbytes, dev) if dev >= 0 else DeviceBuffer(buf.nbytes)
     tiles_x, tiles_y = -(-cols // m["TW"]), -(-rows // m["TH"])
     a = Args()
-    tmap = (C.c_uint8 * 128)()
-    if dev >= 0:
-        dims = (C.c_uint64 * 2)(cols, rows)
-        strides = (C.c_uint64 * 1)(pitch)
-        box = (C.c_uint32 * 2)(m["BW"], m["BH"])
-        check(lib.drc_tensormap_encode(dev, tmap, _TMA_DTYPE[target.dtype.name], 2, buf.ptr, dims,
-                                       strides, box, 0, 2))
-    a.raw(bytes(tmap), 64)
+    a.raw(encode_tensormap(dev, target.dtype.name, buf.ptr, (cols, rows), (pitch,),
+                           (m["BW"], m["BH"])), 64)
     n_ops = max(len(prog.arrays), 1)
     gs_row, gs_col = [0] * n_ops, [0] * n_ops
     for i, (arr, role) in enumerate(zip(prog.arrays, roles)):

@@ -444,3 +444,28 @@ def test_fft_matches_numpy(gpu):
     np.testing.assert_allclose(back.real, x, rtol=1e-10, atol=1e-10)
     lazy = gpu.fft.fft(gpu.array(x) * 2.0)            # forces the lazy operand, like the reference
     np.testing.assert_allclose(lazy.get(), np.fft.fft(x * 2.0), rtol=1e-10, atol=1e-9)
+
+
+@pytest.mark.parametrize("shape", [(256, 192, 320), (1000, 777, 650), (128, 64, 128), (2048, 2048, 2048)])
+def test_dense_matmul_tcgen05(gpu, shape):
+    """A genuine dense float32 `@` runs on the tensor cores (tcgen05, 3xTF32 split) and must still
+    meet the fp32 bar: |C - C_exact| <= 1e-5 * (|A| @ |B|), the usual matmul tolerance."""
+    from delayrepay_b200 import engine
+    m, k, n = shape
+    rng = np.random.default_rng(53)
+    a = rng.standard_normal((m, k)).astype(np.float32)
+    b = rng.standard_normal((k, n)).astype(np.float32)
+    A, B = gpu.array(a), gpu.array(b)
+    before = engine.stats["launches"]
+    got = (A @ B).get()
+    assert any(name[0] == "tcgen05_gemm" for name in engine._kernels), "tensor-core path not taken"
+    exact = a.astype(np.float64) @ b.astype(np.float64)
+    scale = np.abs(a).astype(np.float64) @ np.abs(b).astype(np.float64)
+    assert got.dtype == np.float32 and got.shape == (m, n)
+    assert np.all(np.abs(got - exact) <= 1e-5 * scale)
+    np.testing.assert_allclose(got, a @ b, rtol=1e-5, atol=1e-5 * float(scale.max()))
+    if m <= 1000:       # lazy producers are fused into the operand split pre-pass
+        got2 = ((A * 2.0 + 1.0) @ (B - 0.5)).get()
+        ex2 = (a.astype(np.float64) * 2.0 + 1.0) @ (b.astype(np.float64) - 0.5)
+        sc2 = np.abs(a * 2.0 + 1.0).astype(np.float64) @ np.abs(b - 0.5).astype(np.float64)
+        assert np.all(np.abs(got2 - ex2) <= 1e-5 * sc2)
