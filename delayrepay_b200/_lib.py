@@ -53,6 +53,7 @@ _SIGS = {
     "drc_host_unregister": ([vp], i32),
     "drc_compile": ([C.c_char_p, C.c_char_p, P(C.c_char_p), i32, P(vp), P(sz), P(vp)], i32),
     "drc_free_blob": ([vp], i32),
+    "drc_nvrtc_version": ([P(i32), P(i32), P(C.c_char_p)], i32),
     "drc_module_load": ([i32, vp, sz, P(u64)], i32),
     "drc_module_unload": ([i32, u64], i32),
     "drc_module_get_function": ([i32, u64, C.c_char_p, P(u64)], i32),
@@ -116,6 +117,13 @@ def gpu_available():
         return init() > 0
     except DrcError:
         return False
+
+
+def nvrtc_version():
+    """(major, minor, path) of the NVRTC libdrcuda bound."""
+    ma, mi, path = C.c_int(), C.c_int(), C.c_char_p()
+    check(lib.drc_nvrtc_version(C.byref(ma), C.byref(mi), C.byref(path)))
+    return ma.value, mi.value, (path.value or b"").decode()
 
 
 def compile_cubin(source, name, options):

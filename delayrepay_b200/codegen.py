@@ -16,6 +16,8 @@ import os
 
 import numpy as np
 
+from . import ranges
+
 CTYPE = {
     "?": "bool", "b": "signed char", "B": "unsigned char", "h": "short", "H": "unsigned short",
     "i": "int", "I": "unsigned int", "l": "long long", "L": "unsigned long long",
@@ -186,7 +188,7 @@ def _identity(op, dt):
 
 # --------------------------------------------------------------------------- flat family
 def gen_flat(name, prog, in_class, out_dts, vec_ok, stream, reduce=None, unroll=None,
-             threads=256, min_blocks=None, meta=None):
+             threads=256, min_blocks=None, meta=None, sclasses=None):
     """Contiguous 1-d kernel.  ``reduce`` = None or (op, acc np.dtype, result np.dtype, post).
 
     One copy of the fused body per vector lane (plus one scalar-tail copy): each thread loads
@@ -228,7 +230,7 @@ def gen_flat(name, prog, in_class, out_dts, vec_ok, stream, reduce=None, unroll=
     safe_body = emit_body(prog, fast=False)
     fast_body = emit_body(prog, fast=True) if two_tier else safe_body
     if lockstep:
-        lock_body, lock_uniform = emit_body_lockstep(prog, in_class, V)
+        lock_body, lock_uniform = emit_body_lockstep(prog, in_class, V, sclasses)
     src = []
     w = src.append
     if two_tier:
@@ -258,8 +260,14 @@ def gen_flat(name, prog, in_class, out_dts, vec_ok, stream, reduce=None, unroll=
         w(f"  {A} acc[{U}];")
         w(f"#pragma unroll\n  for (int u = 0; u < {U}; ++u) acc[u] = {_identity(rop, acc_dt)};")
     if lockstep and uses_erf_table(prog):
-        w("  __shared__ float2 dr_erf_tab[DR_ERF_TAB_PAIRS];")
-        w("  dr_erf_tab_stage(dr_erf_tab);")
+        if GEN2:
+            w("  __shared__ float2 dr_erf_tab[3 * DR_ERF2_ROWS];")
+            w("  dr_erf2_tab_stage(dr_erf_tab);")
+        else:
+            w("  __shared__ float2 dr_erf_tab[DR_ERF_TAB_PAIRS];")
+            w("  dr_erf_tab_stage(dr_erf_tab);")
+    if lockstep:
+        w(DR_ONE.format("n"))
     w(f"  const i64 nv = n / {V};")
     w("  const i64 stride = (i64)gridDim.x * blockDim.x;")
 
@@ -286,35 +294,50 @@ def gen_flat(name, prog, in_class, out_dts, vec_ok, stream, reduce=None, unroll=
     if meta is not None:
         meta["smem"] = NS * len(c_inputs) * threads * 16 if staged else 0
     if staged:
-        # operands arrive through an NS-deep shared-memory ring filled by 1-d TMA bulk copies
-        # (one elected thread issues them, an mbarrier per stage counts the bytes): the loads of
-        # tile t+NS-1 are in flight while tile t is evaluated, and no register is held for them
+        # operands arrive through PER-WARP shared-memory rings filled by 1-d TMA bulk copies: lane
+        # 0 of each warp issues the copies of the warp's tile (32 vectors = 512 B per operand) and
+        # an mbarrier per (warp, stage) counts the bytes.  No block-wide barrier in the loop: the
+        # warps of a CTA drift apart, so their divisions (MUFU), polynomials (FMA pipe) and table
+        # look-ups (LSU) overlap instead of arriving at every pipe in phase; NS tiles per warp are
+        # in flight while one is evaluated, and no register is held for them.
         nin = len(c_inputs)
+        WPB = threads // 32
+        SB = nin * 512                                   # bytes per stage
         w("  extern __shared__ __align__(128) unsigned char dr_smem[];")
-        w(f"  __shared__ __align__(8) unsigned long long dr_bar[{NS}];")
-        w(f"  if (threadIdx.x == 0) {{ for (int s = 0; s < {NS}; ++s) dr_mbar_init(&dr_bar[s], 1); dr_fence_barrier_init(); }}")
-        w("  __syncthreads();")
-        w(f"  const i64 ntiles = (nv + {threads - 1}) / {threads};")
-        w("  auto dr_issue = [&](i64 tile, int stage) {")
-        w("    if (tile < ntiles) {")
-        w(f"      const i64 v0 = tile * {threads};")
-        w(f"      const unsigned bytes = (unsigned)(nv - v0 < {threads} ? nv - v0 : {threads}) * 16u;")
-        w(f"      dr_mbar_expect_tx(&dr_bar[stage], bytes * {nin}u);")
+        w(f"  __shared__ __align__(8) unsigned long long dr_bar[{WPB * NS}];")
+        # the shuffle tells the compiler the warp index is warp-uniform: everything derived from
+        # it (addresses, byte counts, barrier words) stays on the uniform datapath
+        w("  const int dr_warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);")
+        w("  const int dr_lane = threadIdx.x & 31;")
+        w(f"  const unsigned dr_bar_s = dr_smem_addr(&dr_bar[dr_warp * {NS}]);")
+        w(f"  const unsigned dr_ring_s = dr_smem_addr(dr_smem) + dr_warp * {NS * SB};")
+        w(f"  if (dr_lane == 0) {{ for (int s = 0; s < {NS}; ++s) dr_mbar_init(&dr_bar[dr_warp * {NS} + s], 1); dr_fence_barrier_init(); }}")
+        w("  __syncwarp();")
+        # tiles are counted in 32 bits: n / (32 * V) < 2^32 for any array that fits in HBM
+        w("  const unsigned ntiles = (unsigned)((nv + 31) / 32);")
+        w("  const unsigned dr_last_bytes = (unsigned)(nv - (i64)(ntiles - 1) * 32) * 16u;")
+        w(f"  const unsigned dr_gw = blockIdx.x * {WPB}u + dr_warp, dr_nw = gridDim.x * {WPB}u;")
+        w("  auto dr_issue = [&](unsigned tile, unsigned stage) {       // lane 0, tile < ntiles")
+        w("    const unsigned bytes = tile == ntiles - 1 ? dr_last_bytes : 512u;")
+        w("    const unsigned bar = dr_bar_s + stage * 8u;")
+        w(f"    const unsigned dst = dr_ring_s + stage * {SB}u;")
+        w(f"    dr_mbar_expect_tx_s(bar, bytes * {nin}u);")
         for slot, (i, a) in enumerate(c_inputs):
-            w(f"      dr_bulk_load(dr_smem + (stage * {nin} + {slot}) * {threads * 16}, in{i} + v0 * {V}, bytes, &dr_bar[stage]);")
-        w("    }")
+            w(f"    dr_bulk_load_s(dst + {slot * 512}u, in{i} + (i64)tile * {32 * V}, bytes, bar);")
         w("  };")
-        w(f"  if (threadIdx.x == 0) {{ for (int k = 0; k < {NS - 1}; ++k) dr_issue(blockIdx.x + (i64)k * gridDim.x, k); }}")
-        w("  int dr_it = 0;")
-        w("  for (i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++dr_it) {")
-        w(f"    const int stage = dr_it % {NS};")
-        w(f"    if (threadIdx.x == 0) dr_issue(tile + (i64){NS - 1} * gridDim.x, (dr_it + {NS - 1}) % {NS});")
-        w(f"    dr_mbar_wait(&dr_bar[stage], (dr_it / {NS}) & 1);")
-        w(f"    const i64 i = tile * {threads} + threadIdx.x;")
-        w("    if (i < nv) {")
+        w(f"  if (dr_lane == 0) {{ for (unsigned k = 0; k < {NS}u; ++k) if (dr_gw + k * dr_nw < ntiles) dr_issue(dr_gw + k * dr_nw, k); }}")
+        w("  unsigned dr_stage = 0, dr_phase = 0;")
+        w("  for (unsigned tile = dr_gw; tile < ntiles; tile += dr_nw) {")
+        w("    dr_mbar_wait_s(dr_bar_s + dr_stage * 8u, dr_phase);")
+        w("    const i64 i = (i64)tile * 32 + dr_lane;")
+        w(f"    const unsigned dr_src = dr_ring_s + dr_stage * {SB}u + dr_lane * 16u;")
         for slot, (i, a) in enumerate(c_inputs):
             w(f"    Vec<{ctype(a.dtype)}, {V}> v{i}[1];")
-            w(f"    v{i}[0] = *reinterpret_cast<const Vec<{ctype(a.dtype)}, {V}>*>(dr_smem + (stage * {nin} + {slot}) * {threads * 16} + threadIdx.x * 16);")
+            w(f"    v{i}[0] = dr_lds16<{ctype(a.dtype)}, {V}>(dr_src + {slot * 512}u);")
+        w("    __syncwarp();             // every lane holds its vector: the stage can be refilled")
+        w(f"    if (tile + {NS}u * dr_nw < ntiles) {{ if (dr_elect()) dr_issue(tile + {NS}u * dr_nw, dr_stage); }}")
+        w(f"    if (++dr_stage == {NS}u) {{ dr_stage = 0; dr_phase ^= 1u; }}")
+        w("    if (i < nv) {")
     elif prefetch:
         # software pipelining: the loads of the NEXT vector are in flight while this one is
         # evaluated (a heavy body with one vector per trip would otherwise expose DRAM latency)
@@ -399,7 +422,6 @@ def gen_flat(name, prog, in_class, out_dts, vec_ok, stream, reduce=None, unroll=
                 w(f"    v{i}[0] = nx{i};")
     if staged:
         w("    }")
-        w("    __syncthreads();          // everyone is done with this stage before it is refilled")
     w("  }")
     # scalar tail: the n - nv*V < V trailing elements, first threads of block 0, precise forms
     if V > 1:
@@ -423,18 +445,31 @@ def gen_flat(name, prog, in_class, out_dts, vec_ok, stream, reduce=None, unroll=
 
 
 _PACKED = {"add": "dr_add4", "subtract": "dr_sub4", "multiply": "dr_mul4"}
+_NOFUSE = {"add": "dr_add4_nofuse", "subtract": "dr_sub4_nofuse"}
+# second generation: accurate-table erf, guards placed by ranges.analyse
+GEN2 = os.environ.get("DR_GEN", "2") != "1"
 _LANE4_FAST = {"true_divide": "dr_div4_fast", "divide": "dr_div4_fast", "sqrt": "dr_sqrt4_fast",
                "log": "dr_log4_f32", "exp": "dr_exp4_f32", "erf": "dr_erf4_tab"}
+_LANE4_R = {"true_divide": "dr_div4_r", "divide": "dr_div4_r", "sqrt": "dr_sqrt4_r",
+            "log": "dr_log4_r", "exp": "dr_exp4_r", "erf": "dr_erf4_gal"}
 if os.environ.get("DR_F64_EXPLOG"):          # previous generation: double-precision exp/log/erf
     _LANE4_FAST.update({"log": "dr_log4_fast", "exp": "dr_exp4_fast", "erf": "dr_erf4_fast"})
-
-
-def uses_erf_table(prog):
-    return _LANE4_FAST["erf"] == "dr_erf4_tab" and any(
-        op == "erf" and loop[0] == np.float32 for op, loop, _, _ in prog.instrs)
+    GEN2 = False
 F32 = np.dtype(np.float32)
 if os.environ.get("DR_F32_NATIVE"):
     _LANE4_FAST.update({"log": "dr_log4_native", "exp": "dr_exp4_native", "erf": "dr_erf4_native"})
+    GEN2 = False
+
+
+def uses_erf_table(prog):
+    return (GEN2 or _LANE4_FAST["erf"] == "dr_erf4_tab") and any(
+        op == "erf" and loop[0] == np.float32 for op, loop, _, _ in prog.instrs)
+
+
+# 1.0f the compiler cannot see through (derived from a kernel parameter whose sign bit is never
+# set; a form based on blockDim.x is folded through __launch_bounds__): fma(a, one, b) == a + b
+# exactly and is never contracted with the multiply that produced a
+DR_ONE = "  const float dr_one = __int_as_float(0x3f800000 | (int)((unsigned long long){0} >> 63));"
 
 
 def lockstep_ok(prog, V):
@@ -446,7 +481,7 @@ def has_lane_fast(prog):
     return any(op in _LANE4_FAST and loop[0] == F32 for op, loop, _, _ in prog.instrs)
 
 
-def emit_body_lockstep(prog, in_class, V=4):
+def emit_body_lockstep(prog, in_class, V=4, sclasses=None):
     """Lane-array form of the fused body: every SSA value is `T tK[4]` (or a plain scalar when
     it only depends on scalars / broadcast operands) and each instruction is applied to all
     four lanes at once -- packed f32x2 for float32 + - *, the dr_*4_fast lane functions for
@@ -454,6 +489,13 @@ def emit_body_lockstep(prog, in_class, V=4):
     lines = []
     uniform = {}
     packed_products = set()          # temps produced by a packed multiply
+    an = ranges.analyse(prog, in_class, sclasses, set(_LANE4_R)) if (GEN2 and V == 4) else None
+    if an is not None and (an.pos_inputs or an.any_inputs):
+        # one min/max tree over every lane of every operand the fast forms rely on
+        tests = [f"dr_rg.pos4(v{i}[u].v);" for i in an.pos_inputs]
+        tests += [f"dr_rg.any4(v{i}[u].v);" for i in an.any_inputs]
+        oks = (["dr_rg.ok_pos()"] if an.pos_inputs else []) + (["dr_rg.ok_any()"] if an.any_inputs else [])
+        lines.append("{ DrRange dr_rg; " + " ".join(tests) + f" bad = bad || !({' && '.join(oks)}); }}")
 
     def is_uniform(r):
         if r[0] == "s":
@@ -485,13 +527,20 @@ def emit_body_lockstep(prog, in_class, V=4):
             # ptxas fuses mul.rn.f32x2 + add/sub.rn.f32x2 into FFMA2 even though both carry an
             # explicit .rn (observed, CUDA 12.9; the scalar forms are never fused).  An add
             # that consumes a packed product therefore stays scalar: a*b+c must round twice.
-            fn = "__fadd_rn" if op == "add" else "__fsub_rn"
-            lines.append(f"_Pragma(\"unroll\") for (int e = 0; e < {V}; ++e) "
-                         f"t{k}[e] = {fn}({lane(args[0])}, {lane(args[1])});")
+            if GEN2:
+                lines.append(f"{_NOFUSE[op]}({arr(args[0])}, {arr(args[1])}, t{k}, dr_one);")
+            else:
+                fn = "__fadd_rn" if op == "add" else "__fsub_rn"
+                lines.append(f"_Pragma(\"unroll\") for (int e = 0; e < {V}; ++e) "
+                             f"t{k}[e] = {fn}({lane(args[0])}, {lane(args[1])});")
         elif same and op in _PACKED and V == 4:
             lines.append(f"{_PACKED[op]}({arr(args[0])}, {arr(args[1])}, t{k});")
             if op == "multiply":
                 packed_products.add(me)
+        elif same and an is not None and op in _LANE4_R and k in an.check:
+            flags = ", ".join("true" if c else "false" for c in an.check[k])
+            extra = ", dr_erf_tab" if op == "erf" else ""
+            lines.append(f"{_LANE4_R[op]}<{flags}>({', '.join(arr(r) for r in args)}, t{k}, bad{extra});")
         elif same and op in _LANE4_FAST and V == 4:
             extra = ", dr_erf_tab" if _LANE4_FAST[op] == "dr_erf4_tab" else ""
             lines.append(f"{_LANE4_FAST[op]}({', '.join(arr(r) for r in args)}, t{k}, bad{extra});")
@@ -822,6 +871,7 @@ def gen_stencil(name, prog, roles, out_dt, TW=248, TH=32, NS=4, threads=496):
     w(f"        const Vec<{T}, {V}> keep = rowp0;")
     w(f"        Vec<{T}, {V}> r0;")
     if lock_body is not None:
+        w("      " + DR_ONE.format("(long long)g.h"))
         w("        bool bad = false;")
         for line in lock_body:
             w(f"        {line}")

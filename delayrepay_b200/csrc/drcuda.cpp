@@ -340,11 +340,68 @@ int drc_host_unregister(void* hptr) {
 }
 
 // ---------------------------------------------------------------- compile + load
+// NVRTC is bound with dlopen by ABSOLUTE path, newest toolkit first.  A plain -lnvrtc binds to
+// whichever libnvrtc.so.12 the process loaded first -- PyTorch's wheel preloads its own 12.8
+// copy, whose ptxas generates measurably worse SASS for the packed f32x2 kernels (24 extra
+// negation FADDs per Black-Scholes vector, profiles/r1_bs_v8*) than the image's 12.9 toolkit.
+#define NVRTC_FNS(X) X(nvrtcCreateProgram) X(nvrtcCompileProgram) X(nvrtcGetProgramLogSize) \
+  X(nvrtcGetProgramLog) X(nvrtcDestroyProgram) X(nvrtcGetCUBINSize) X(nvrtcGetCUBIN)        \
+  X(nvrtcGetErrorString) X(nvrtcVersion)
+#define X(fn) static decltype(&fn) q_##fn = nullptr;
+NVRTC_FNS(X)
+#undef X
+static std::once_flag g_nvrtc_once;
+static std::string g_nvrtc_path, g_nvrtc_err;
+
+static void load_nvrtc() {
+  std::vector<std::string> cand;
+  if (const char* e = getenv("DRC_NVRTC")) cand.push_back(e);
+  if (const char* e = getenv("CUDA_HOME")) cand.push_back(std::string(e) + "/lib64/libnvrtc.so.12");
+  cand.push_back("/usr/local/cuda/lib64/libnvrtc.so.12");
+  cand.push_back("/usr/local/cuda/lib64/libnvrtc.so");
+  cand.push_back("libnvrtc.so.12");
+  cand.push_back("libnvrtc.so");
+  void* h = nullptr;
+  for (const auto& c : cand) {
+    h = dlopen(c.c_str(), RTLD_NOW | RTLD_LOCAL);
+    if (h) { g_nvrtc_path = c; break; }
+  }
+  if (!h) { g_nvrtc_err = "libnvrtc not found (set DRC_NVRTC or CUDA_HOME)"; return; }
+#define X(fn) q_##fn = (decltype(&fn))dlsym(h, #fn); if (!q_##fn) g_nvrtc_err = "missing NVRTC symbol " #fn;
+  NVRTC_FNS(X)
+#undef X
+}
+static int need_nvrtc() {
+  std::call_once(g_nvrtc_once, load_nvrtc);
+  if (!g_nvrtc_err.empty()) return fail("%s", g_nvrtc_err.c_str());
+  return 0;
+}
+#define nvrtcCreateProgram q_nvrtcCreateProgram
+#define nvrtcCompileProgram q_nvrtcCompileProgram
+#define nvrtcGetProgramLogSize q_nvrtcGetProgramLogSize
+#define nvrtcGetProgramLog q_nvrtcGetProgramLog
+#define nvrtcDestroyProgram q_nvrtcDestroyProgram
+#define nvrtcGetCUBINSize q_nvrtcGetCUBINSize
+#define nvrtcGetCUBIN q_nvrtcGetCUBIN
+#define nvrtcGetErrorString q_nvrtcGetErrorString
+
+// version * 1000 + minor * 10 of the NVRTC in use and the path it was loaded from
+int drc_nvrtc_version(int* major, int* minor, const char** path) {
+  if (need_nvrtc()) return 1;
+  int ma = 0, mi = 0;
+  q_nvrtcVersion(&ma, &mi);
+  if (major) *major = ma;
+  if (minor) *minor = mi;
+  if (path) *path = g_nvrtc_path.c_str();
+  return 0;
+}
+
 int drc_compile(const char* source, const char* name, const char* const* options,
                 int num_options, void** cubin, size_t* cubin_len, char** log) {
   *cubin = nullptr;
   *cubin_len = 0;
   if (log) *log = nullptr;
+  if (need_nvrtc()) return 1;
   nvrtcProgram prog;
   nvrtcResult r = nvrtcCreateProgram(&prog, source, name, 0, nullptr, nullptr);
   if (r != NVRTC_SUCCESS) return fail("nvrtcCreateProgram: %s", nvrtcGetErrorString(r));

@@ -13,7 +13,7 @@ import weakref
 
 import numpy as np
 
-from . import _lib, codegen, planner
+from . import _lib, codegen, planner, ranges
 from ._lib import check, lib
 from .device import DeviceArray, DeviceBuffer, current_device
 
@@ -24,8 +24,10 @@ NVRTC_OPTIONS = [f"--gpu-architecture={ARCH}", "--std=c++17", "--fmad=false",
 CACHE_DIR = os.environ.get("DR_CACHE_DIR", os.path.join(_HERE, "_cache"))
 DUMP_SRC = os.environ.get("DR_DUMP_SRC")
 
-with open(os.path.join(_HERE, "csrc", "prelude.cuh")) as _f:
+with open(os.path.join(_HERE, "csrc", "math_tables.cuh")) as _f:      # generated coefficient tables
     PRELUDE = _f.read()
+with open(os.path.join(_HERE, "csrc", "prelude.cuh")) as _f:
+    PRELUDE += _f.read()
 
 stats = {"compiled": 0, "disk_hits": 0, "mem_hits": 0, "launches": 0, "compile_ms": 0.0}
 
@@ -256,12 +258,17 @@ def run_program(prog, outs, reduce=None, inplace=False):
         + sum(o.dtype.itemsize for o in outs)
     stream_hint = (not inplace) and lay.total * max(moved, 1) > 2 * st.l2_bytes
     if lay.family == "flat":
+        # float32 scalars are classified by magnitude ('n' = 2^-24 <= |s| < 2^24): the interval
+        # analysis that places the range guards (ranges.py) may rely on the class, so it is
+        # part of the structural key; values themselves stay kernel arguments
+        scl = ranges.scalar_classes(prog) if codegen.has_lane_fast(prog) else None
         key = ("flat", prog.key(), lay.in_class, tuple(d.str for d in out_dts), lay.vec_ok,
-               stream_hint, red_key, inplace)
+               stream_hint, red_key, inplace, scl)
         gen_reduce = None if reduce is None else (reduce[0], reduce[1], reduce[2], None)
         meta = {}
         kern = get_kernel(key, lambda name: codegen.gen_flat(
-            name, prog, lay.in_class, out_dts, lay.vec_ok, stream_hint, gen_reduce, meta=meta), meta)
+            name, prog, lay.in_class, out_dts, lay.vec_ok, stream_hint, gen_reduce, meta=meta,
+            sclasses=scl), meta)
         smem = kern.meta.get("smem", 0)
         a = Args()
         a.i64(lay.total)

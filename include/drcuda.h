@@ -66,6 +66,9 @@ int drc_host_unregister(void* hptr);
 int drc_compile(const char* source, const char* name, const char* const* options,
                 int num_options, void** cubin, size_t* cubin_len, char** log);
 int drc_free_blob(void* blob);
+/* Version and path of the NVRTC the library bound (dlopen by absolute path, toolkit first: the
+ * first libnvrtc.so.12 a process happens to load is not necessarily the toolkit's). */
+int drc_nvrtc_version(int* major, int* minor, const char** path);
 int drc_module_load(int dev, const void* cubin, size_t cubin_len, uint64_t* module);
 int drc_module_unload(int dev, uint64_t module);
 int drc_module_get_function(int dev, uint64_t module, const char* entry, uint64_t* func);
