@@ -18,6 +18,9 @@ import numpy as np
 
 from . import ranges
 
+with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "math_tables.cuh")) as _f:
+    ERF2_ROWS = int([ln.split()[2] for ln in _f if ln.startswith("#define DR_ERF2_ROWS")][0])
+
 CTYPE = {
     "?": "bool", "b": "signed char", "B": "unsigned char", "h": "short", "H": "unsigned short",
     "i": "int", "I": "unsigned int", "l": "long long", "L": "unsigned long long",
@@ -188,7 +191,7 @@ def _identity(op, dt):
 
 # --------------------------------------------------------------------------- flat family
 def gen_flat(name, prog, in_class, out_dts, vec_ok, stream, reduce=None, unroll=None,
-             threads=256, min_blocks=None, meta=None, sclasses=None):
+             threads=None, min_blocks=None, meta=None, sclasses=None):
     """Contiguous 1-d kernel.  ``reduce`` = None or (op, acc np.dtype, result np.dtype, post).
 
     One copy of the fused body per vector lane (plus one scalar-tail copy): each thread loads
@@ -209,6 +212,18 @@ def gen_flat(name, prog, in_class, out_dts, vec_ok, stream, reduce=None, unroll=
     U = unroll
     S = "true" if stream else "false"
     two_tier = has_fast_path(prog)
+    lockstep = lockstep_ok(prog, V) and os.environ.get("DR_LOCKSTEP", "1") != "0"
+    c_inputs = [(i, a) for i, (a, c) in enumerate(zip(arrays, in_class)) if c == "c"]
+    staged = (U == 1 and V > 1 and body_weight(prog) >= 2 and c_inputs
+              and all(a.dtype.itemsize * V == 16 for _, a in c_inputs)
+              and os.environ.get("DR_STAGED", "1") != "0")
+    # table-driven erf in a staged kernel: ONE 1024-thread CTA per SM, so that 16 bank-private
+    # replicas of the table (84 KiB) fit beside the per-warp operand rings
+    erf_rep = 16 if (staged and lockstep and GEN2 and uses_erf_table(prog)
+                     and os.environ.get("DR_ERF_REP", "16") != "1") else 1
+    if threads is None:
+        threads = int(os.environ.get("DR_THREADS", 0)) or (1024 if erf_rep == 16 else 256)
+    NS = int(os.environ.get("DR_STAGES", 0)) or (2 if erf_rep == 16 else 3)
 
     params = ["const i64 n"]
     for i, a in enumerate(arrays):
@@ -224,13 +239,12 @@ def gen_flat(name, prog, in_class, out_dts, vec_ok, stream, reduce=None, unroll=
         params += [f"{A}* __restrict__ partials", "unsigned int* __restrict__ counter",
                    f"{ctype(res_dt)}* __restrict__ result", "const double post_scale"]
 
-    lockstep = lockstep_ok(prog, V) and os.environ.get("DR_LOCKSTEP", "1") != "0"
     if lockstep:
         two_tier = two_tier or has_lane_fast(prog)
     safe_body = emit_body(prog, fast=False)
     fast_body = emit_body(prog, fast=True) if two_tier else safe_body
     if lockstep:
-        lock_body, lock_uniform = emit_body_lockstep(prog, in_class, V, sclasses)
+        lock_body, lock_uniform = emit_body_lockstep(prog, in_class, V, sclasses, erf_rep)
     src = []
     w = src.append
     if two_tier:
@@ -250,7 +264,7 @@ def gen_flat(name, prog, in_class, out_dts, vec_ok, stream, reduce=None, unroll=
         w("  return res;")
         w("}")
     min_blocks = min_blocks or int(os.environ.get("DR_MINBLOCKS", 0)) or (
-        4 if (lockstep and body_weight(prog) >= 2) else None)     # measured best on B200 (C2)
+        (1024 // threads) if (lockstep and body_weight(prog) >= 2) else None)   # 64 registers
     lb = f"__launch_bounds__({threads}" + (f", {min_blocks})" if min_blocks else ")")
     w(f'extern "C" __global__ void {lb} {name}({", ".join(params)}) {{')
     for i, (a, c) in enumerate(zip(arrays, in_class)):
@@ -260,9 +274,11 @@ def gen_flat(name, prog, in_class, out_dts, vec_ok, stream, reduce=None, unroll=
         w(f"  {A} acc[{U}];")
         w(f"#pragma unroll\n  for (int u = 0; u < {U}; ++u) acc[u] = {_identity(rop, acc_dt)};")
     if lockstep and uses_erf_table(prog):
-        if GEN2:
+        if GEN2 and erf_rep == 16:
+            pass            # carved out of dynamic shared memory behind the operand rings (below)
+        elif GEN2:
             w("  __shared__ float2 dr_erf_tab[3 * DR_ERF2_ROWS];")
-            w("  dr_erf2_tab_stage(dr_erf_tab);")
+            w("  dr_erf2_tab_stage<1>(dr_erf_tab);")
         else:
             w("  __shared__ float2 dr_erf_tab[DR_ERF_TAB_PAIRS];")
             w("  dr_erf_tab_stage(dr_erf_tab);")
@@ -284,15 +300,12 @@ def gen_flat(name, prog, in_class, out_dts, vec_ok, stream, reduce=None, unroll=
         else:
             w(f"{p}val[e] = ({A}){_operand_name(prog.roots[0])};")
 
-    c_inputs = [(i, a) for i, (a, c) in enumerate(zip(arrays, in_class)) if c == "c"]
-    staged = (U == 1 and V > 1 and body_weight(prog) >= 2 and c_inputs
-              and all(a.dtype.itemsize * V == 16 for _, a in c_inputs)
-              and os.environ.get("DR_STAGED", "1") != "0")
-    NS = int(os.environ.get("DR_STAGES", 3))
     prefetch = (not staged) and U == 1 and body_weight(prog) >= 2 \
         and os.environ.get("DR_PREFETCH", "0") != "0"
+    ring_bytes = NS * len(c_inputs) * threads * 16 if staged else 0
     if meta is not None:
-        meta["smem"] = NS * len(c_inputs) * threads * 16 if staged else 0
+        meta["smem"] = ring_bytes + (3 * ERF2_ROWS * 16 * 8 if erf_rep == 16 else 0)
+        meta["threads"] = threads
     if staged:
         # operands arrive through PER-WARP shared-memory rings filled by 1-d TMA bulk copies: lane
         # 0 of each warp issues the copies of the warp's tile (32 vectors = 512 B per operand) and
@@ -304,6 +317,9 @@ def gen_flat(name, prog, in_class, out_dts, vec_ok, stream, reduce=None, unroll=
         WPB = threads // 32
         SB = nin * 512                                   # bytes per stage
         w("  extern __shared__ __align__(128) unsigned char dr_smem[];")
+        if erf_rep == 16:
+            w(f"  float2* const dr_erf_tab = reinterpret_cast<float2*>(dr_smem + {ring_bytes});")
+            w("  dr_erf2_tab_stage<16>(dr_erf_tab);")
         w(f"  __shared__ __align__(8) unsigned long long dr_bar[{WPB * NS}];")
         # the shuffle tells the compiler the warp index is warp-uniform: everything derived from
         # it (addresses, byte counts, barrier words) stays on the uniform datapath
@@ -481,7 +497,7 @@ def has_lane_fast(prog):
     return any(op in _LANE4_FAST and loop[0] == F32 for op, loop, _, _ in prog.instrs)
 
 
-def emit_body_lockstep(prog, in_class, V=4, sclasses=None):
+def emit_body_lockstep(prog, in_class, V=4, sclasses=None, erf_rep=1):
     """Lane-array form of the fused body: every SSA value is `T tK[4]` (or a plain scalar when
     it only depends on scalars / broadcast operands) and each instruction is applied to all
     four lanes at once -- packed f32x2 for float32 + - *, the dr_*4_fast lane functions for
@@ -539,6 +555,8 @@ def emit_body_lockstep(prog, in_class, V=4, sclasses=None):
                 packed_products.add(me)
         elif same and an is not None and op in _LANE4_R and k in an.check:
             flags = ", ".join("true" if c else "false" for c in an.check[k])
+            if op == "erf":
+                flags += f", {erf_rep}"
             extra = ", dr_erf_tab" if op == "erf" else ""
             lines.append(f"{_LANE4_R[op]}<{flags}>({', '.join(arr(r) for r in args)}, t{k}, bad{extra});")
         elif same and op in _LANE4_FAST and V == 4:
@@ -812,8 +830,12 @@ def gen_stencil(name, prog, roles, out_dt, TW=248, TH=32, NS=4, threads=496):
         if r[0] == "b":
             w(f"  const {ctype(a.dtype)} x{i} = *reinterpret_cast<const {ctype(a.dtype)}*>(in{i});")
     if lock_body is not None and uses_erf_table(prog):
-        w("  __shared__ float2 dr_erf_tab[DR_ERF_TAB_PAIRS];")
-        w("  dr_erf_tab_stage(dr_erf_tab);")
+        if GEN2:
+            w("  __shared__ float2 dr_erf_tab[3 * DR_ERF2_ROWS];")
+            w("  dr_erf2_tab_stage<1>(dr_erf_tab);")
+        else:
+            w("  __shared__ float2 dr_erf_tab[DR_ERF_TAB_PAIRS];")
+            w("  dr_erf_tab_stage(dr_erf_tab);")
     w(f"  const int tx = tid % {cols_per_row}, ty = tid / {cols_per_row};")
     w("  auto issue = [&](int tile, int stage) {")
     w("    if (tile < g.ntiles) {")

@@ -270,6 +270,7 @@ def run_program(prog, outs, reduce=None, inplace=False):
             name, prog, lay.in_class, out_dts, lay.vec_ok, stream_hint, gen_reduce, meta=meta,
             sclasses=scl), meta)
         smem = kern.meta.get("smem", 0)
+        threads = kern.meta.get("threads", 256)
         a = Args()
         a.i64(lay.total)
         for arr in prog.arrays:
@@ -284,9 +285,10 @@ def run_program(prog, outs, reduce=None, inplace=False):
         if smem > 40 * 1024 and dev >= 0 and not kern.meta.get("smem_set"):
             check(lib.drc_func_set_max_dynamic_smem(dev, kern.func(dev), smem))
             kern.meta["smem_set"] = True
-        grid = _grid_for(kern, dev, 256, -(-lay.total // vec), smem)
+        grid = _grid_for(kern, dev, threads, -(-lay.total // vec), smem)
     else:
         smem = 0
+        threads = 256
         wide = lay.total >= (1 << 32) or any(
             abs(s) * n >= (1 << 62) for stv in lay.in_strides for s, n in zip(stv, lay.shape))
         key = ("nd", prog.key(), len(lay.shape), lay.in_class, tuple(d.str for d in out_dts),
@@ -312,7 +314,7 @@ def run_program(prog, outs, reduce=None, inplace=False):
         a.ptr(st.counter_ptr)
         a.ptr(reduce[4].ptr)
         a.f64(reduce[3])
-    launch(kern, dev, grid, 256, a, smem=smem)
+    launch(kern, dev, grid, threads, a, smem=smem)
 
 
 def evaluate_nodes(nodes, outs=None, inplace=False):

@@ -44,7 +44,7 @@ def mp_vec(fn, x):
 
 
 # ----------------------------------------------------------------------------------------- erf
-ERF_LOW_EXP = -20                     # rows start at 2^-20
+ERF_LOW_EXP = -12                     # rows start at 2^-12 (225 rows: 16 bank-private copies = 84 KiB)
 ERF_PER_BINADE = 16
 ERF_ROWS = (2 - ERF_LOW_EXP) * ERF_PER_BINADE + 1       # + row 0
 ERF_BASE = ((127 + ERF_LOW_EXP) << 4) - 1               # (bits >> 19) - ERF_BASE = row, clamped at 0
