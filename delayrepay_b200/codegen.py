@@ -283,6 +283,7 @@ def gen_flat(name, prog, in_class, out_dts, vec_ok, stream, reduce=None, unroll=
             w("  __shared__ float2 dr_erf_tab[DR_ERF_TAB_PAIRS];")
             w("  dr_erf_tab_stage(dr_erf_tab);")
     if lockstep:
+        emit_explog_stage(w, prog)
         w(DR_ONE.format("n"))
     w(f"  const i64 nv = n / {V};")
     w("  const i64 stride = (i64)gridDim.x * blockDim.x;")
@@ -467,7 +468,10 @@ GEN2 = os.environ.get("DR_GEN", "2") != "1"
 _LANE4_FAST = {"true_divide": "dr_div4_fast", "divide": "dr_div4_fast", "sqrt": "dr_sqrt4_fast",
                "log": "dr_log4_f32", "exp": "dr_exp4_f32", "erf": "dr_erf4_tab"}
 _LANE4_R = {"true_divide": "dr_div4_r", "divide": "dr_div4_r", "sqrt": "dr_sqrt4_r",
-            "log": "dr_log4_r", "exp": "dr_exp4_r", "erf": "dr_erf4_gal"}
+            "log": "dr_log4_t", "exp": "dr_exp4_t", "erf": "dr_erf4_gal"}
+if os.environ.get("DR_EXPLOG_POLY"):         # table-free exp / log (17 / 30 FMA cycles per element)
+    _LANE4_R.update({"log": "dr_log4_r", "exp": "dr_exp4_r"})
+_TABLE_ARG = {"dr_erf4_gal": ", dr_erf_tab", "dr_exp4_t": ", dr_exp_tab", "dr_log4_t": ", dr_log_tab"}
 if os.environ.get("DR_F64_EXPLOG"):          # previous generation: double-precision exp/log/erf
     _LANE4_FAST.update({"log": "dr_log4_fast", "exp": "dr_exp4_fast", "erf": "dr_erf4_fast"})
     GEN2 = False
@@ -475,6 +479,25 @@ F32 = np.dtype(np.float32)
 if os.environ.get("DR_F32_NATIVE"):
     _LANE4_FAST.update({"log": "dr_log4_native", "exp": "dr_exp4_native", "erf": "dr_erf4_native"})
     GEN2 = False
+
+
+def explog_tables(prog):
+    """(uses exp table, uses log table) for the lane forms of generation 2."""
+    if not GEN2:
+        return False, False
+    ops = {op for op, loop, _, _ in prog.instrs if loop[0] == np.float32}
+    return ("exp" in ops and _LANE4_R["exp"] == "dr_exp4_t",
+            "log" in ops and _LANE4_R["log"] == "dr_log4_t")
+
+
+def emit_explog_stage(w, prog, indent="  "):
+    ue, ul = explog_tables(prog)
+    if ue:
+        w(f"{indent}__shared__ float2 dr_exp_tab[DR_EXP2_SMEM_PAIRS];")
+    if ul:
+        w(f"{indent}__shared__ float4 dr_log_tab[DR_LOG2_SMEM_QUADS];")
+    if ue or ul:
+        w(f"{indent}dr_explog_tab_stage({'dr_exp_tab' if ue else 'nullptr'}, {'dr_log_tab' if ul else 'nullptr'});")
 
 
 def uses_erf_table(prog):
@@ -557,7 +580,7 @@ def emit_body_lockstep(prog, in_class, V=4, sclasses=None, erf_rep=1):
             flags = ", ".join("true" if c else "false" for c in an.check[k])
             if op == "erf":
                 flags += f", {erf_rep}"
-            extra = ", dr_erf_tab" if op == "erf" else ""
+            extra = _TABLE_ARG.get(_LANE4_R[op], "")
             lines.append(f"{_LANE4_R[op]}<{flags}>({', '.join(arr(r) for r in args)}, t{k}, bad{extra});")
         elif same and op in _LANE4_FAST and V == 4:
             extra = ", dr_erf_tab" if _LANE4_FAST[op] == "dr_erf4_tab" else ""
@@ -829,6 +852,8 @@ def gen_stencil(name, prog, roles, out_dt, TW=248, TH=32, NS=4, threads=496):
     for i, (a, r) in enumerate(zip(arrays, roles)):
         if r[0] == "b":
             w(f"  const {ctype(a.dtype)} x{i} = *reinterpret_cast<const {ctype(a.dtype)}*>(in{i});")
+    if lock_body is not None:
+        emit_explog_stage(w, prog)
     if lock_body is not None and uses_erf_table(prog):
         if GEN2:
             w("  __shared__ float2 dr_erf_tab[3 * DR_ERF2_ROWS];")
