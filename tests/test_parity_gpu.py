@@ -166,6 +166,62 @@ def test_division_sqrt_log_on_random_bit_patterns(gpu):
         assert_bits_equal((1.0 / gpu.array(d)).get(), (1.0 / d).astype(np.float32), "reciprocal")
 
 
+def _hostile(rng, n, positive=False):
+    """Mostly moderate values with every special class sprinkled in."""
+    x = rng.uniform(0.01, 100.0, n).astype(np.float32)
+    if not positive:
+        x *= rng.choice(np.array([-1, 1], np.float32), n)
+    special = np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 1e-45, -1e-42, 3.4e38, -3e38, 1e-38,
+                        2.0 ** -31, 2.0 ** 30, 2.0 ** -30, 1.0, -1.0, 5e-324], dtype=np.float32)
+    idx = rng.choice(n, n // 16, replace=False)
+    x[idx] = rng.choice(special, idx.size)
+    return x
+
+
+def test_guard_placement_keeps_arithmetic_exact_on_hostile_inputs(gpu):
+    """The interval analysis (ranges.py) drops per-operation range tests where it can prove the
+    fast forms' preconditions from ONE combined test of the inputs; a vector that fails the
+    combined test must take the precise path.  Exact operations must stay bit-exact for zeros,
+    negatives, subnormals, huge values, inf and nan anywhere in the inputs."""
+    rng = np.random.default_rng(77)
+    n = (1 << 18) + 3
+    a, b, c = _hostile(rng, n), _hostile(rng, n), _hostile(rng, n, positive=True)
+
+    def f(xp, a, b, c):
+        q = (a / b + c * 0.5) / (0.3 * xp.sqrt(c))          # the Black-Scholes d1 shape
+        return q, q - 0.3 * xp.sqrt(c), xp.sqrt(a / b)
+    with np.errstate(all="ignore"):
+        got = f(gpu, gpu.array(a), gpu.array(b), gpu.array(c))
+        gpu.evaluate(*got)
+        want = f(np, a, b, c)
+        for g, w, nm in zip(got, want, ("d1-like", "d2-like", "sqrt(a/b)")):
+            assert_bits_equal(g.get(), w.astype(np.float32), nm)
+
+
+def test_generation2_exp_log_erf_over_their_whole_domains(gpu):
+    rng = np.random.default_rng(5)
+    n = 1 << 20
+    with np.errstate(all="ignore"):
+        x = np.concatenate([rng.uniform(-104, 89, n), rng.uniform(-1, 1, n // 4)]).astype(np.float32)
+        assert_close_to_numpy_or_truth(np.exp(gpu.array(x)).get(), np.exp(x), np.exp, (x,), 2, "exp wide")
+        x = np.exp(rng.uniform(-87, 88, n)).astype(np.float32)
+        x = np.concatenate([x, rng.uniform(0.5, 2.0, n // 2).astype(np.float32),
+                            np.float32(1) + np.arange(-2048, 2048, dtype=np.float32) * np.float32(2.0 ** -24)])
+        assert_close_to_numpy_or_truth(np.log(gpu.array(x)).get(), np.log(x), np.log, (x,), 2, "log wide")
+        x = (np.exp(rng.uniform(-60, 2.5, n)) * rng.choice([-1.0, 1.0], n)).astype(np.float32)
+        x = np.concatenate([x, np.linspace(-6, 6, n // 2, dtype=np.float32),
+                            np.array([0.0, -0.0, 1e-45, -1e-45, 4.0, 3.9999998, 1e30, -1e30], np.float32)])
+        got, want = erf(gpu.array(x)).get(), erf(x)
+        assert_close_to_numpy_or_truth(got, want, erf, (x,), 2, "erf wide")
+        assert np.array_equal(np.signbit(got), np.signbit(want)), "erf sign (incl. -0)"
+        # inside a fused chain the table forms see arbitrary finite intermediates
+        y = rng.uniform(-30, 30, n).astype(np.float32)
+        got = erf(np.exp(gpu.array(y) * 0.1) - 2.0).get()
+        truth = erf(np.exp(y.astype(np.float64) * np.float64(np.float32(0.1))) - 2.0)
+        # the subtraction amplifies exp's last-place error; bound the absolute error instead
+        np.testing.assert_allclose(got, truth, rtol=0, atol=2e-6)
+
+
 # ------------------------------------------------------------------ C2: Black-Scholes
 def _bs_truth(S, K, T, r=0.02, v=0.30):
     S, K, T = (a.astype(np.float64) for a in (S, K, T))

@@ -97,7 +97,12 @@ def test_all_workloads_generate_and_compile(dry):
     dr.evaluate(call, put)
     assert len(dry) == n0 + 1, "call and put must share ONE fused kernel"
     kern = dry[-1][0]
-    assert "dr_erf4_tab(" in kern.source and "dr_bulk_load(" in kern.source   # staged + lockstep
+    body = kern.source[kern.source.index('extern "C" __global__'):]
+    # staged per-warp TMA rings + lockstep body with the guards the interval analysis left
+    assert "dr_bulk_load_s(" in body and "dr_elect()" in body and "__syncthreads();          //" not in body
+    assert body.count("dr_div4_r<false, false>(") == 2 and "dr_erf4_gal<false, 16>(" in body
+    assert "dr_log4_t<false>(" in body and "dr_sqrt4_r<false>(" in body and "dr_exp4_t<true>(" in body
+    assert "dr_rg.pos4(v0[u].v); dr_rg.pos4(v1[u].v); dr_rg.pos4(v2[u].v);" in body
     i = wl.make_inputs("l2", 4096)
     a, b = dr.array(i["a"]), dr.array(i["b"])
     n0 = len(dry)
@@ -112,6 +117,47 @@ def test_all_workloads_generate_and_compile(dry):
     wl.nbody_acc(dr, dr.array(i["pos"]), dr.array(i["m"])).run()
     for kern, grid, block in dry:
         assert kern.cubin[:4] == b"\x7fELF"
+
+
+def test_interval_analysis_places_guards(dry):
+    """ranges.analyse: operands tested once at the top, per-operation tests only where the
+    propagated interval does not imply the fast form's precondition."""
+    from delayrepay_b200 import codegen, ranges
+    F = np.float32
+    S, K, T, X = (dr.NPArray(dr.DeviceArray.empty((4096,), F)) for _ in range(4))
+    call, put = wl.black_scholes(dr, S, K, T)
+    prog = planner.build_program([call, put])
+    guarded = set(codegen._LANE4_R)
+    an = ranges.analyse(prog, "ccc", ranges.scalar_classes(prog), guarded)
+    assert an.pos_inputs == [0, 1, 2] and an.any_inputs == []
+    ops = {k: prog.instrs[k][0] for k in an.check}
+    by_op = {}
+    for k, flags in an.check.items():
+        by_op.setdefault(ops[k], []).append(flags)
+    assert by_op.get("true_divide", by_op.get("divide")) == [(False, False), (False, False)]
+    assert by_op["sqrt"] == [(False,)] and by_op["log"] == [(False,)]
+    assert by_op["exp"] == [(True,)], "|-r T| < 87 does not follow from T < 2^30"
+    assert by_op["erf"] == [(False,), (False,)], "finite arguments: no nan test"
+    # a scalar outside 2^-24 .. 2^24 is not trusted: the second division keeps its tests
+    call, put = wl.black_scholes(dr, S, K, T, v=1e-30)
+    prog = planner.build_program([call, put])
+    scl = ranges.scalar_classes(prog)
+    assert "u" in scl
+    an = ranges.analyse(prog, "ccc", scl, guarded)
+    divs = [f for k, f in an.check.items() if prog.instrs[k][0] in ("true_divide", "divide")]
+    assert divs[0] == (False, False) and divs[1] != (False, False)
+    # nothing is known about an operand that feeds no guarded operation directly
+    prog = planner.build_program([np.exp(X) / (X + 1.0)])
+    an = ranges.analyse(prog, "c", ranges.scalar_classes(prog), guarded)
+    assert an.pos_inputs == [] and an.any_inputs == []
+    assert all(all(f) for f in an.check.values())
+    # the abstract domain itself
+    a, b = ranges.R(-30, 30, neg=False), ranges.R(-24, 24)
+    m = ranges._mul(a, b)
+    assert (m.lo, m.hi, m.zero) == (-55, 54, False) and m.neg and m.pos
+    s_ = ranges._addsub(ranges.R(-25, 7, zero=True), m, False)
+    assert s_.zero and not s_.nz and s_.lo == -55 - 24 and s_.hi == 55
+    assert ranges._mul(ranges.R(0, 100), ranges.R(0, 100)) is None, "may overflow: unknown"
 
 
 def test_cubin_is_sm100a_with_vector_ldst(dry, tmp_path):
