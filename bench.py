@@ -111,7 +111,7 @@ def reference_arm(args, rank, world):
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": "black_scholes_f32", "log2_options_per_step": log2n,
+        "config": {"workload": "black_scholes_f32_call_put", "log2_options_per_step": log2n,
                    "note": "bounded sample of the 2^30 workload on host cores"},
         "cpu_baseline": {"value": value, "unit": "options/s", "cores": 1, "kind": "port",
                          "sample": f"2^{log2n} options/step, oracle/refcpu.py (unfused NumPy per "
