@@ -69,7 +69,7 @@ def body_weight(prog):
     return sum(1 for op, _, _, _ in prog.instrs if op in _HEAVY)
 
 
-def emit_expr(op, loop, out_dt, args, arg_dts, fast=False, relaxed=False):
+def emit_expr(op, loop, out_dt, args, arg_dts, fast=False, relaxed=False, pow_mode=None):
     """C expression for one SSA instruction; ``args`` are C expressions of dtype arg_dts.
     ``fast``: use the branch-free flag-raising float32 forms (see prelude, dr_*_fast)."""
     cast_args = []
@@ -120,6 +120,10 @@ def emit_expr(op, loop, out_dt, args, arg_dts, fast=False, relaxed=False):
     if op == "invert":
         return f"(!{a[0]})" if k == "b" else f"(({O})(~{a[0]}))"
     if op == "power":
+        if pow_mode == "rsqrt3":                 # x ** -1.5 inside a contraction (relaxed_pow_modes)
+            return f"dr_rsqrt3_relaxed({a[0]})"
+        if pow_mode == "rsqrt":
+            return f"dr_rsqrt_relaxed({a[0]})"
         if relaxed and loop[0] == np.float32:
             return f"dr_pow_relaxed({a[0]}, {a[1]})"
         return f"dr_pow({a[0]}, {a[1]})" if k == "f" else f"dr_ipow<{T}>({a[0]}, {a[1]})"
@@ -144,7 +148,23 @@ def _operand_name(ref):
     return {"a": "x", "s": "s", "t": "t"}[ref[0]] + str(ref[1])
 
 
-def emit_body(prog, fast=False, relaxed=False):
+def relaxed_pow_modes(prog):
+    """{instr index: mode} for float32 `x ** s` with a scalar exponent of -1.5 / -0.5.  Inside a
+    contraction only the reduced sum is observable (rtol 1e-5), so these become one MUFU.RSQ
+    (relative error 2^-22.4) without the per-element exponent test; the exponent VALUE is part of
+    the kernel key of the callers that use this."""
+    out = {}
+    for k, (op, loop, out_dt, args) in enumerate(prog.instrs):
+        if op == "power" and loop[0] == np.float32 and args[1][0] == "s":
+            v = float(prog.scalars[args[1][1]][0])
+            if v == -1.5:
+                out[k] = "rsqrt3"
+            elif v == -0.5:
+                out[k] = "rsqrt"
+    return out
+
+
+def emit_body(prog, fast=False, relaxed=False, pow_modes=None):
     """The fused scalar body: `const T tK = expr;` lines over x<i> (arrays), s<j> (scalars).
     ``relaxed``: inside a contraction, where only the reduced result is observable (rtol bar),
     float32 pow with a uniform exponent may take its reciprocal-square-root form."""
@@ -153,7 +173,7 @@ def emit_body(prog, fast=False, relaxed=False):
         exprs = [_operand_name(r) for r in args]
         dts = [prog.dtypes[r] for r in args]
         lines.append(f"const {ctype(out_dt)} t{k} = "
-                     f"{emit_expr(op, loop, out_dt, exprs, dts, fast, relaxed)};")
+                     f"{emit_expr(op, loop, out_dt, exprs, dts, fast, relaxed, (pow_modes or {}).get(k))};")
     return lines
 
 
@@ -960,16 +980,19 @@ def gen_stencil(name, prog, roles, out_dt, TW=248, TH=32, NS=4, threads=496):
 
 
 # --------------------------------------------------------------------------- skinny contraction
-def gen_mm_skinny(name, prog, roles, t_dt, n_out, threads=256, tile_k=256):
+def gen_mm_skinny(name, prog, roles, t_dt, n_out, threads=128, tile_k=256, rows=4, pow_modes=None):
     """out[i, 0:n_out] (+)= sum_k A(i, k) * B[k, 0:n_out] where A is a fused elementwise program
     whose array operands each vary along rows only ('r'), along k only ('c') or not at all ('b')
-    -- the all-pairs pattern x[None, :] - x[:, None] ... of the n-body workload.  One thread per
-    output row, B and the k-varying operands staged through shared memory per k-tile (broadcast
-    reads), accumulation in registers; grid.y splits K, each split writes its own partial block
-    (deterministic: the partials are summed by a second fused kernel, no atomics).  B's last
-    column may be a virtual column of ones (row sum of A folded into the same pass)."""
+    -- the all-pairs pattern x[None, :] - x[:, None] ... of the n-body workload.  Register tile:
+    every thread owns `rows` output rows (rows threads apart, so the final stores coalesce) and
+    evaluates the producer for all of them against one k at a time, so the k-varying operands and
+    the B row are read from shared memory ONCE per `rows` pairs (broadcast reads: every lane the
+    same address).  grid.y splits K, each split writes its own partial block (deterministic: the
+    partials are summed by a second fused kernel, no atomics).  B's last column may be a virtual
+    column of ones (row sum of A folded into the same pass)."""
     arrays, scalars = prog.arrays, prog.scalars
     T = ctype(t_dt)
+    R = rows
     n_ops = max(len(arrays), 1)
     src = []
     w = src.append
@@ -980,48 +1003,68 @@ def gen_mm_skinny(name, prog, roles, t_dt, n_out, threads=256, tile_k=256):
     for j, (_, dt) in enumerate(scalars):
         params.append(f"const {ctype(dt)} s{j}")
     params += ["const char* __restrict__ B", f"{T}* __restrict__ partial"]
-    body = emit_body(prog, fast=False, relaxed=True)
+    body = emit_body(prog, fast=False, relaxed=True, pow_modes=pow_modes)
     w(f'extern "C" __global__ void __launch_bounds__({threads}) {name}({", ".join(params)}) {{')
     cols = [i for i, r in enumerate(roles) if r == "c"]
+    rws = [i for i, r in enumerate(roles) if r == "r"]
     for i in cols:
         w(f"  __shared__ {ctype(arrays[i].dtype)} sh{i}[{tile_k}];")
-    w(f"  __shared__ {T} shB[{tile_k}][{n_out}];")
+    w(f"  __shared__ __align__(16) {T} shB[{tile_k}][{n_out}];")
     w("  const int tid = threadIdx.x;")
-    w(f"  const i64 row = (i64)blockIdx.x * {threads} + tid;")
-    w("  const i64 rr = row < g.M ? row : g.M - 1;")
+    w(f"  const i64 row0 = (i64)blockIdx.x * {threads * R} + tid;")
     for i, (a, r) in enumerate(zip(arrays, roles)):
         A = ctype(a.dtype)
         if r == "b":
             w(f"  const {A} x{i} = *reinterpret_cast<const {A}*>(in{i});")
-        elif r == "r":
-            w(f"  const {A} x{i} = *reinterpret_cast<const {A}*>(in{i} + rr * g.sr[{i}]);")
-    w(f"  {T} acc[{n_out}];")
-    w(f"#pragma unroll\n  for (int n = 0; n < {n_out}; ++n) acc[n] = ({T})0;")
+    for i in rws:
+        A = ctype(arrays[i].dtype)
+        w(f"  {A} xr{i}[{R}];")
+    w(f"#pragma unroll\n  for (int r = 0; r < {R}; ++r) {{")
+    w(f"    const i64 row = row0 + r * {threads};")
+    w("    const i64 rr = row < g.M ? row : g.M - 1;")
+    for i in rws:
+        A = ctype(arrays[i].dtype)
+        w(f"    xr{i}[r] = *reinterpret_cast<const {A}*>(in{i} + rr * g.sr[{i}]);")
+    w("  }")
+    w(f"  {T} acc[{R}][{n_out}];")
+    w(f"#pragma unroll\n  for (int r = 0; r < {R}; ++r)")
+    w(f"#pragma unroll\n    for (int n = 0; n < {n_out}; ++n) acc[r][n] = ({T})0;")
     w("  const i64 k0 = (i64)blockIdx.y * g.kchunk;")
     w("  const i64 k1 = k0 + g.kchunk < g.K ? k0 + g.kchunk : g.K;")
     w(f"  for (i64 kt = k0; kt < k1; kt += {tile_k}) {{")
-    w("    const i64 kk = kt + tid < k1 ? kt + tid : k1 - 1;")
+    w(f"    for (int t = tid; t < {tile_k}; t += {threads}) {{")
+    w("      const i64 kk = kt + t < k1 ? kt + t : k1 - 1;")
     for i in cols:
         A = ctype(arrays[i].dtype)
-        w(f"    sh{i}[tid] = *reinterpret_cast<const {A}*>(in{i} + kk * g.sc[{i}]);")
-    w(f"#pragma unroll\n    for (int n = 0; n < {n_out}; ++n)")
-    w(f"      shB[tid][n] = n < g.n_real ? *reinterpret_cast<const {T}*>(B + kk * g.b_rs + n * g.b_cs) : ({T})1;")
+        w(f"      sh{i}[t] = *reinterpret_cast<const {A}*>(in{i} + kk * g.sc[{i}]);")
+    w(f"#pragma unroll\n      for (int n = 0; n < {n_out}; ++n)")
+    w(f"        shB[t][n] = n < g.n_real ? *reinterpret_cast<const {T}*>(B + kk * g.b_rs + n * g.b_cs) : ({T})1;")
+    w("    }")
     w("    __syncthreads();")
     w(f"    const int lim = (int)(k1 - kt < {tile_k} ? k1 - kt : {tile_k});")
-    w("#pragma unroll 4")
+    w("#pragma unroll 2")
     w("    for (int j = 0; j < lim; ++j) {")
     for i in cols:
         w(f"      const {ctype(arrays[i].dtype)} x{i} = sh{i}[j];")
+    w(f"      {T} bj[{n_out}];")
+    w(f"#pragma unroll\n      for (int n = 0; n < {n_out}; ++n) bj[n] = shB[j][n];")
+    w(f"#pragma unroll\n      for (int r = 0; r < {R}; ++r) {{")
+    for i in rws:
+        w(f"        const {ctype(arrays[i].dtype)} x{i} = xr{i}[r];")
     for line in body:
-        w(f"      {line}")
+        w(f"        {line}")
     root = _store_expr(prog, prog.roots[0], t_dt)
-    w(f"      const {T} a_ik = {root};")
-    w(f"#pragma unroll\n      for (int n = 0; n < {n_out}; ++n) acc[n] = fma(a_ik, shB[j][n], acc[n]);")
+    w(f"        const {T} a_ik = {root};")
+    w(f"#pragma unroll\n        for (int n = 0; n < {n_out}; ++n) acc[r][n] = fma(a_ik, bj[n], acc[r][n]);")
+    w("      }")
     w("    }")
     w("    __syncthreads();")
     w("  }")
-    w("  if (row < g.M) {")
-    w(f"#pragma unroll\n    for (int n = 0; n < {n_out}; ++n) partial[((i64)blockIdx.y * g.M + row) * {n_out} + n] = acc[n];")
+    w(f"#pragma unroll\n  for (int r = 0; r < {R}; ++r) {{")
+    w(f"    const i64 row = row0 + r * {threads};")
+    w("    if (row < g.M) {")
+    w(f"#pragma unroll\n      for (int n = 0; n < {n_out}; ++n) partial[((i64)blockIdx.y * g.M + row) * {n_out} + n] = acc[r][n];")
+    w("    }")
     w("  }")
     w("}")
     return "\n".join(src) + "\n"

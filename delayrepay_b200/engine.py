@@ -606,8 +606,11 @@ def _try_mm_skinny(node, pa, m, k, n, res_dt, with_rowsum=None):
     kchunk = -(-k // ksplit)
     kchunk = -(-kchunk // 256) * 256
     ksplit = -(-k // kchunk)
-    key = ("mm_skinny", pa.key(), tuple(roles), res_dt.str, n_out)
-    kern = get_kernel(key, lambda name: codegen.gen_mm_skinny(name, pa, roles, res_dt, n_out))
+    pow_modes = codegen.relaxed_pow_modes(pa)
+    R, TH = 4, 128
+    key = ("mm_skinny", pa.key(), tuple(roles), res_dt.str, n_out, tuple(sorted(pow_modes.items())), R, TH)
+    kern = get_kernel(key, lambda name: codegen.gen_mm_skinny(
+        name, pa, roles, res_dt, n_out, threads=TH, rows=R, pow_modes=pow_modes))
     partial = DeviceArray.empty((ksplit, m, n_out), res_dt, dev if dev >= 0 else None)
     a = Args()
     n_ops = max(len(pa.arrays), 1)
@@ -623,7 +626,7 @@ def _try_mm_skinny(node, pa, m, k, n, res_dt, with_rowsum=None):
         a.scalar(val, dt)
     a.ptr(b_dev.ptr)
     a.ptr(partial.ptr)
-    launch(kern, dev, (-(-m // 256), ksplit, 1), 256, a)
+    launch(kern, dev, (-(-m // (TH * R)), ksplit, 1), TH, a)
     total = ReduceEx(np.add, NPArray(partial), 0, False)._force()        # (m, n_out), fixed order
     node._stamp = _stamp_of(pa)
     if rowsum is not None:
