@@ -220,6 +220,9 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dr.set_device(local_rank)
     dev = local_rank
+    # host side of the e2e path: threads and pinned staging buffers on the GPU's NUMA node
+    from delayrepay_b200.device import bind_to_device_numa
+    numa_cpus = None if os.environ.get("DR_NO_NUMA_BIND") else bind_to_device_numa(local_rank)
 
     def barrier():
         dr.synchronize()
@@ -326,7 +329,8 @@ def main():
                "note": "pinned host buffers -> dr.map_chunks(black_scholes): chunked H2D / fused "
                        "kernel / D2H on three streams, every byte crosses PCIe inside the timed "
                        "region; wall clock, max over ranks.  eager_ms_per_step = dr.array(h) -> "
-                       "evaluate -> .get(out=), copies and kernel strictly serial"}
+                       "evaluate -> .get(out=), copies and kernel strictly serial",
+               "host_numa_cpus": None if numa_cpus is None else len(numa_cpus)}
 
     if rank != 0:
         if world > 1:

@@ -37,6 +37,7 @@ _SIGS = {
     "drc_device_count": ([P(i32)], i32),
     "drc_device_attr": ([i32, P(i32), P(i32), P(i32), P(sz), P(i32), P(i32)], i32),
     "drc_device_name": ([i32, C.c_char_p, sz], i32),
+    "drc_device_pci_bus_id": ([i32, C.c_char_p, sz], i32),
     "drc_mem_info": ([i32, P(sz), P(sz)], i32),
     "drc_malloc_async": ([i32, i32, sz, P(u64)], i32),
     "drc_free_async": ([i32, i32, u64], i32),

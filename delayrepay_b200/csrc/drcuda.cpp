@@ -40,7 +40,7 @@ int fail(const char* fmt, ...) {
 #define DRC_STR(x) #x
 #define DRV_FUNCS(X)                                                                         \
   X(cuInit) X(cuGetErrorString) X(cuGetErrorName) X(cuDeviceGetCount) X(cuDeviceGet)         \
-  X(cuDeviceGetName) X(cuDeviceGetAttribute) X(cuDeviceTotalMem) X(cuDevicePrimaryCtxRetain) \
+  X(cuDeviceGetName) X(cuDeviceGetPCIBusId) X(cuDeviceGetAttribute) X(cuDeviceTotalMem) X(cuDevicePrimaryCtxRetain) \
   X(cuDevicePrimaryCtxRelease) X(cuCtxSetCurrent) X(cuCtxGetCurrent) X(cuStreamCreate)       \
   X(cuStreamDestroy) X(cuStreamSynchronize) X(cuCtxSynchronize) X(cuMemGetInfo)              \
   X(cuMemAllocAsync) X(cuMemFreeAsync) X(cuDeviceGetDefaultMemPool) X(cuMemPoolSetAttribute) \
@@ -232,6 +232,13 @@ int drc_device_attr(int dev, int* sm_count, int* cc_major, int* cc_minor, size_t
 int drc_device_name(int dev, char* buf, size_t buflen) {
   USE(dev);
   CU(p_cuDeviceGetName(buf, (int)buflen, g_devs[dev].dev));
+  return 0;
+}
+
+// "0000:1b:00.0"-style PCI address: the key to /sys/bus/pci/devices/<id>/numa_node, local_cpulist
+int drc_device_pci_bus_id(int dev, char* buf, size_t buflen) {
+  USE(dev);
+  CU(p_cuDeviceGetPCIBusId(buf, (int)buflen, g_devs[dev].dev));
   return 0;
 }
 

@@ -18,10 +18,42 @@ from ._lib import lib, check
 _current = {"dev": 0, "dry": False, "fake_ptr": 0x7F0000000000}
 
 
-def set_device(dev):
-    """Select the device new arrays are created on (one process per GPU: LOCAL_RANK)."""
+def set_device(dev, bind_numa=False):
+    """Select the device new arrays are created on (one process per GPU: LOCAL_RANK).
+    ``bind_numa``: also restrict this process to the CPUs of the GPU's NUMA node, so that pinned
+    staging buffers allocated afterwards are node-local and H2D/D2H copies of several ranks do
+    not cross the socket interconnect (the host<->device path is PCIe- and host-DRAM-bound)."""
     _lib.init()
     _current["dev"] = int(dev)
+    if bind_numa:
+        bind_to_device_numa(int(dev))
+
+
+def bind_to_device_numa(dev):
+    """sched_setaffinity to /sys/bus/pci/devices/<gpu>/local_cpulist.  Returns the CPU set used,
+    or None when the topology is not exposed (single-node hosts, containers without sysfs)."""
+    import ctypes as C
+    import os
+    buf = C.create_string_buffer(64)
+    try:
+        check(lib.drc_device_pci_bus_id(dev, buf, 64))
+        bdf = buf.value.decode().lower()
+        with open(f"/sys/bus/pci/devices/{bdf}/local_cpulist") as f:
+            text = f.read().strip()
+        cpus = set()
+        for part in text.split(","):
+            if "-" in part:
+                lo, hi = part.split("-")
+                cpus.update(range(int(lo), int(hi) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except (OSError, ValueError, _lib.DrcError):
+        return None
 
 
 def current_device():

@@ -179,49 +179,81 @@ def dev_state(dev):
 _PACK_ALIGN = 8
 
 
-class Args:
-    """Packs kernel arguments into one blob + offsets (drc_launch_packed)."""
+_SCALAR_FMT = {"f4": ("f", 4), "f8": ("d", 8), "i4": ("i", 4), "i8": ("q", 8), "u4": ("I", 4),
+               "u8": ("Q", 8), "i2": ("h", 2), "u2": ("H", 2), "i1": ("b", 1), "u1": ("B", 1),
+               "b1": ("?", 1)}
+_arg_layouts = {}            # format string -> (struct.Struct, ctypes offsets array, count)
 
-    __slots__ = ("buf", "offsets")
+
+class Args:
+    """Kernel arguments: a struct format (explicit padding, natural alignment per argument --
+    the CUDA parameter layout) plus the values; packed once at launch.  The compiled Struct and
+    the ctypes offset table are cached per format string, i.e. per kernel signature."""
+
+    __slots__ = ("fmt", "vals", "size", "offsets")
 
     def __init__(self):
-        self.buf = bytearray()
-        self.offsets = []
+        self.fmt, self.vals, self.size, self.offsets = [], [], 0, []
 
-    def _align(self, a):
-        pad = (-len(self.buf)) % a
+    def _put(self, code, size, align, value):
+        pad = (-self.size) % align
         if pad:
-            self.buf += b"\0" * pad
+            self.fmt.append(f"{pad}x")
+            self.size += pad
+        self.offsets.append(self.size)
+        self.fmt.append(code)
+        self.vals.append(value)
+        self.size += size
 
     def raw(self, data, align):
-        self._align(align)
-        self.offsets.append(len(self.buf))
-        self.buf += data
+        self._put(f"{len(data)}s", len(data), align, bytes(data))
 
     def i64(self, v):
-        self.raw(int(v).to_bytes(8, "little", signed=True), 8)
+        self._put("q", 8, 8, int(v))
 
     def ptr(self, v):
-        self.raw(int(v).to_bytes(8, "little", signed=False), 8)
+        self._put("Q", 8, 8, int(v))
 
     def f64(self, v):
-        self.raw(np.float64(v).tobytes(), 8)
+        self._put("d", 8, 8, float(v))
 
     def scalar(self, value, dtype):
-        data = np.asarray(value, dtype=dtype).tobytes()
-        self.raw(data, max(len(data), 1))
+        dt = np.dtype(dtype)
+        hit = _SCALAR_FMT.get(dt.str[1:])
+        if hit is not None and dt.kind != "c":
+            code, size = hit
+            if dt.kind == "f":
+                # route through the dtype so that float32 rounding / inf / nan match NumPy's
+                value = float(dt.type(value))
+            elif dt.kind == "b":
+                value = bool(value)
+            else:
+                value = int(dt.type(value))
+            self._put(code, size, size, value)
+        else:
+            data = np.asarray(value, dtype=dt).tobytes()
+            self.raw(data, max(min(len(data), 8), 1))
+
+    def pack(self):
+        key = "".join(self.fmt)
+        lay = _arg_layouts.get(key)
+        if lay is None:
+            import struct
+            lay = _arg_layouts[key] = (struct.Struct("<" + key),
+                                       (C.c_uint32 * len(self.offsets))(*self.offsets),
+                                       len(self.offsets))
+        return lay[0].pack(*self.vals), lay[1], lay[2]
 
 
 def launch(kernel, dev, grid, block, args, smem=0, stream=0, cluster=1):
     if dev < 0:
         dry_log.append((kernel, grid, block))
         return
-    blob = bytes(args.buf)
-    offs = (C.c_uint32 * len(args.offsets))(*args.offsets)
+    blob, offs, n = args.pack()
     gx, gy, gz = (tuple(grid) + (1, 1))[:3] if not isinstance(grid, int) else (grid, 1, 1)
     bx, by, bz = (tuple(block) + (1, 1))[:3] if not isinstance(block, int) else (block, 1, 1)
     check(lib.drc_launch_packed(dev, stream, kernel.func(dev), gx, gy, gz, bx, by, bz, smem,
-                                cluster, blob, offs, len(args.offsets)))
+                                cluster, blob, offs, n))
     stats["launches"] += 1
 
 

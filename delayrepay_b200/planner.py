@@ -18,6 +18,17 @@ import numpy as np
 from .device import DeviceArray
 
 
+_DSTR = {}
+
+
+def _dstr(dt):
+    """dtype -> its '<f4'-style string, cached (np.dtype.str builds a new str on every access)."""
+    s = _DSTR.get(dt)
+    if s is None:
+        s = _DSTR[dt] = dt.str
+    return s
+
+
 class Program:
     """SSA program of one fused region.
 
@@ -37,10 +48,11 @@ class Program:
 
     def key(self):
         """Structure only: no sizes, pointers or scalar values."""
-        return (tuple(a.dtype.str for a in self.arrays),
-                tuple(dt.str for _, dt in self.scalars),
-                tuple((op, tuple(d.str for d in loop), out.str, args)
-                      for op, loop, out, args in self.instrs),
+        ds = _dstr
+        return (tuple([ds(a.dtype) for a in self.arrays]),
+                tuple([ds(dt) for _, dt in self.scalars]),
+                tuple([(op, tuple([ds(d) for d in loop]), ds(out), args)
+                       for op, loop, out, args in self.instrs]),
                 tuple(self.roots))
 
 

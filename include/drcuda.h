@@ -37,6 +37,9 @@ int drc_device_count(int* count);
 int drc_device_attr(int dev, int* sm_count, int* cc_major, int* cc_minor,
                     size_t* total_mem, int* l2_bytes, int* max_smem_optin);
 int drc_device_name(int dev, char* buf, size_t buflen);
+/* PCI address ("0000:1b:00.0"): lets the host side pin its threads and its pinned staging
+ * memory to the GPU's NUMA node (/sys/bus/pci/devices/<id>/local_cpulist). */
+int drc_device_pci_bus_id(int dev, char* buf, size_t buflen);
 int drc_mem_info(int dev, size_t* free_bytes, size_t* total_bytes);
 
 /* ---- memory: stream-ordered pool -----------------------------------------------------
