@@ -94,6 +94,11 @@ class Memoiser(type):
 def reset():
     """Forget every memoised node  [delayarray.py:234-236]."""
     Memoiser._cache.clear()
+    try:
+        from . import engine
+        engine._plans.clear()
+    except ImportError:
+        pass
 
 
 def _layout_of(arr):
@@ -373,6 +378,80 @@ def resolve_loop(ufunc, kids):
     return hit
 
 
+# --------------------------------------------------------------------------- plan signatures
+# Every elementwise node carries, from construction, a STRUCTURAL SIGNATURE of the expression
+# below it (`_psig`: op names, loop dtypes, the layout of each array leaf, and how operands are
+# shared between sub-expressions -- no values, no addresses) and the tuple of its distinct
+# operand nodes in first-use order (`_pops`).  engine.evaluate_nodes keys a cache of PREPARED
+# LAUNCHES on the roots' signatures: a hit skips planning, layout resolution and kernel lookup
+# and only packs pointers and scalar values (the reference recompiles per expression object,
+# SURVEY.md section 3.2; here a repeated expression costs capture + one launch).
+_PLAN_MAX_OPERANDS = 24
+
+
+def _leaf_sig(leaf):
+    """Layout signature of an array leaf (None: not on the device yet / not eligible)."""
+    arr = leaf.array
+    c = leaf.__dict__.get("_psig_cache")
+    if c is not None and c[0] is arr:
+        return c[1]
+    if not isinstance(arr, DeviceArray):
+        arr = leaf.__dict__.get("_dev")
+        if arr is None:
+            return None
+    sig = ("L", arr.shape, arr.strides, arr.dtype.str, (arr.offset % 16) == 0, arr.dev)
+    leaf._psig_cache = (leaf.array, sig)
+    return sig
+
+
+def _merge_ops(ops, more):
+    """Append the operands of `more` that are not in `ops` yet (identity); returns the merged
+    tuple and, per operand of `more`, its index in it -- the sharing pattern."""
+    merged = list(ops)
+    idx = []
+    for o in more:
+        for j, m in enumerate(merged):
+            if m is o:
+                idx.append(j)
+                break
+        else:
+            idx.append(len(merged))
+            merged.append(o)
+    return tuple(merged), tuple(idx)
+
+
+def _plan_info(tag, kids):
+    """(_psig, _pops) of a node with children `kids`; (None, None) when not eligible."""
+    parts = [tag]
+    ops = ()
+    for k in kids:
+        kind = k.kind
+        if kind == "scalar":
+            ks, kops = ("S", k.weak_type.__name__ if k.weak_type is not None else k.dtype.str), (k,)
+        elif kind == "leaf":
+            if type(k) is not NPArray:
+                return None, None
+            ks, kops = _leaf_sig(k), (k,)
+        elif kind == "ewise":
+            d = k.__dict__
+            ks, kops = d.get("_psig"), d.get("_pops")
+            if d.get("array") is not None:      # materialised producer: the planner cuts here
+                return None, None
+        else:
+            return None, None                    # reductions / contractions are cut points
+        if ks is None:
+            return None, None
+        if not ops:
+            ops = kops
+            parts.append(ks)
+        else:
+            ops, idx = _merge_ops(ops, kops)
+            parts.append((ks, idx))
+    if len(ops) > _PLAN_MAX_OPERANDS:
+        return None, None
+    return hash(tuple(parts)), ops
+
+
 class _Elementwise(NumpyEx, Funcable):
     """Shared body of the three elementwise node classes."""
 
@@ -394,6 +473,7 @@ class _Elementwise(NumpyEx, Funcable):
                     shp = tuple(np.broadcast_shapes(*[kk.shape for kk in kids]))
                     break
         self.shape = shp
+        self._psig, self._pops = _plan_info((self.op, self.loop, shp), kids)
 
     @classmethod
     def _memo_key(cls, func, *kids):
@@ -439,6 +519,7 @@ class WhereEx(NumpyEx):
         out = np.result_type(*sig)
         self.loop, self.dtype = (np.dtype(bool), out, out), out
         self.shape = np.broadcast_shapes(cond.shape, a.shape, b.shape)
+        self._psig, self._pops = _plan_info(("where", self.loop, self.shape), self.children)
 
     @classmethod
     def _memo_key(cls, *kids):
@@ -463,6 +544,7 @@ class CastEx(NumpyEx):
         src = arg.dtype if arg.dtype is not None else np.result_type(arg.weak_type)
         self.loop = (src,)
         self.shape = arg.shape
+        self._psig, self._pops = _plan_info(("cast", self.loop, self.dtype, self.shape), self.children)
 
     @classmethod
     def _memo_key(cls, arg, dtype):

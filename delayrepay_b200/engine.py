@@ -305,6 +305,7 @@ def run_program(prog, outs, reduce=None, inplace=False):
         threads = kern.meta.get("threads", 256)
         a = Args()
         a.i64(lay.total)
+        head = ("i64", lay.total)
         for arr in prog.arrays:
             a.ptr(arr.ptr)
         for val, dt in prog.scalars:
@@ -332,7 +333,8 @@ def run_program(prog, outs, reduce=None, inplace=False):
         operands = list(lay.in_strides) + (list(lay.out_strides) if reduce is None else [])
         if not operands:
             operands = [(0,) * len(lay.shape)]
-        a.raw(_geo_blob(lay.total, lay.shape, operands), 8)
+        head = ("raw", _geo_blob(lay.total, lay.shape, operands))
+        a.raw(head[1], 8)
         for arr in prog.arrays:
             a.ptr(arr.ptr)
         for val, dt in prog.scalars:
@@ -347,17 +349,140 @@ def run_program(prog, outs, reduce=None, inplace=False):
         a.ptr(reduce[4].ptr)
         a.f64(reduce[3])
     launch(kern, dev, grid, threads, a, smem=smem)
+    return kern, grid, threads, smem, head, (scl if lay.family == "flat" else None)
+
+
+# --------------------------------------------------------------------------- prepared launches
+# Plan cache: roots' structural signatures (delayarray._plan_info) -> everything a launch needs
+# except pointers and scalar values.  Only plain elementwise regions with fresh outputs.
+_plans = {}
+_PLAN_CACHE = os.environ.get("DR_PLAN_CACHE", "1") != "0"
+_PLAN_LIMIT = 1024
+
+
+class _Plan:
+    __slots__ = ("kern", "grid", "threads", "smem", "head", "arr_idx", "sc_idx", "sc_dt", "leaf_sigs",
+                 "shape", "out_dts", "dev", "scl")
+
+
+def _plan_key(nodes):
+    """(key, operand nodes) of the roots, or (None, None) when any root is not eligible."""
+    if len(nodes) == 1:
+        d = nodes[0].__dict__
+        sig = d.get("_psig")
+        if sig is None:
+            return None, None
+        return (sig, nodes[0].shape, nodes[0].dtype), d["_pops"]
+    from .delayarray import _merge_ops
+    parts, ops = [], ()
+    for n in nodes:
+        d = n.__dict__
+        sig = d.get("_psig")
+        if sig is None:
+            return None, None
+        if not ops:
+            ops = d["_pops"]
+            parts.append((sig, n.shape, n.dtype))
+        else:
+            ops, idx = _merge_ops(ops, d["_pops"])
+            parts.append((sig, n.shape, n.dtype, idx))
+    return tuple(parts), ops
+
+
+def _plan_launch(plan, ops):
+    """Launch a prepared plan against the current operands; returns (outs, stamp) or None when
+    an operand no longer has the layout (or scalar class) the plan was made for."""
+    from .delayarray import _leaf_sig
+    arrays = []
+    for i, want in zip(plan.arr_idx, plan.leaf_sigs):
+        leaf = ops[i]
+        if _leaf_sig(leaf) != want:
+            return None
+        arrays.append(leaf._force())
+    if plan.scl is not None:
+        for j, (i, dt) in enumerate(zip(plan.sc_idx, plan.sc_dt)):
+            if ranges.scalar_class(ops[i].val, dt) != plan.scl[j]:
+                return None
+    dev = plan.dev
+    outs = [DeviceArray.empty(plan.shape, dt, dev if dev >= 0 else None) for dt in plan.out_dts]
+    a = Args()
+    if plan.head[0] == "i64":
+        a.i64(plan.head[1])
+    else:
+        a.raw(plan.head[1], 8)
+    for arr in arrays:
+        a.ptr(arr.ptr)
+    for i, dt in zip(plan.sc_idx, plan.sc_dt):
+        a.scalar(ops[i].val, dt)
+    for o in outs:
+        a.ptr(o.ptr)
+    launch(plan.kern, dev, plan.grid, plan.threads, a, smem=plan.smem)
+    seen, stamp = set(), []
+    for arr in arrays:
+        b = arr.buf
+        if id(b) not in seen:
+            seen.add(id(b))
+            stamp.append((weakref.ref(b), b.version))
+    stats["plan_hits"] = stats.get("plan_hits", 0) + 1
+    return outs, stamp
+
+
+def _plan_record(key, ops, prog, outs, rec):
+    """Remember the launch `rec` of `prog` under `key` if every kernel operand maps to one of
+    the roots' operand nodes."""
+    from .delayarray import _leaf_sig
+    kern, grid, threads, smem, head, scl = rec
+    arr_idx, leaf_sigs = [], []
+    for arr in prog.arrays:
+        for i, o in enumerate(ops):
+            if o.kind == "leaf" and o._force() is arr:
+                sig = _leaf_sig(o)
+                if sig is None:
+                    return
+                arr_idx.append(i)
+                leaf_sigs.append(sig)
+                break
+        else:
+            return
+    sc_idx = []
+    for node in prog.scalar_nodes:
+        for i, o in enumerate(ops):
+            if o is node:
+                sc_idx.append(i)
+                break
+        else:
+            return
+    if len(_plans) >= _PLAN_LIMIT:
+        _plans.clear()
+    p = _Plan()
+    p.kern, p.grid, p.threads, p.smem, p.head, p.scl = kern, grid, threads, smem, head, scl
+    p.arr_idx, p.leaf_sigs, p.sc_idx = tuple(arr_idx), tuple(leaf_sigs), tuple(sc_idx)
+    p.sc_dt = tuple(dt for _, dt in prog.scalars)
+    p.shape, p.out_dts, p.dev = tuple(outs[0].shape), tuple(o.dtype for o in outs), outs[0].dev
+    _plans[key] = p
 
 
 def evaluate_nodes(nodes, outs=None, inplace=False):
     """Fuse ``nodes`` (same iteration shape) into one kernel; returns the output arrays."""
+    key = ops = None
+    if outs is None and not inplace and _PLAN_CACHE:
+        key, ops = _plan_key(nodes)
+        if key is not None:
+            plan = _plans.get(key)
+            if plan is not None:
+                done = _plan_launch(plan, ops)
+                if done is not None:
+                    return done
     prog = planner.build_program(nodes)
-    if outs is None:
+    fresh = outs is None
+    if fresh:
         dev = prog.arrays[0].dev if prog.arrays else current_device()
         outs = [DeviceArray.empty(prog.shape, n.dtype, dev) for n in nodes]
     else:
         prog.shape = tuple(outs[0].shape)
-    run_program(prog, outs, inplace=inplace)
+    rec = run_program(prog, outs, inplace=inplace)
+    if key is not None and rec is not None and fresh and prog.arrays:
+        _plan_record(key, ops, prog, outs, rec)
     stamp = _stamp_of(prog)
     return outs, stamp
 

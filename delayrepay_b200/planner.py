@@ -38,10 +38,12 @@ class Program:
     roots  : list of operand refs, one per requested output
     """
 
-    __slots__ = ("arrays", "scalars", "instrs", "roots", "shape", "leaf_bufs", "dtypes")
+    __slots__ = ("arrays", "scalars", "instrs", "roots", "shape", "leaf_bufs", "dtypes",
+                 "scalar_nodes")
 
     def __init__(self):
         self.arrays, self.scalars, self.instrs, self.roots = [], [], [], []
+        self.scalar_nodes = []      # the Scalar node behind each entry of `scalars` (plan cache)
         self.shape = ()
         self.leaf_bufs = []
         self.dtypes = {}            # operand ref -> np.dtype
@@ -85,6 +87,7 @@ def build_program(roots):
         if idx is None:
             idx = scalar_slot[k] = len(prog.scalars)
             prog.scalars.append((dtype.type(node.val), dtype))
+            prog.scalar_nodes.append(node)
         r = ("s", idx)
         prog.dtypes[r] = dtype
         return r

@@ -222,6 +222,52 @@ def test_generation2_exp_log_erf_over_their_whole_domains(gpu):
         np.testing.assert_allclose(got, truth, rtol=0, atol=2e-6)
 
 
+def test_plan_cache_replays_are_exact(gpu):
+    """engine._plans: a repeated expression structure launches a prepared plan (no planning);
+    values, operand sharing patterns, layouts and scalar classes may change between replays."""
+    from delayrepay_b200 import engine
+    rng = np.random.default_rng(123)
+    n = 4099
+    x, y, z = (rng.standard_normal(n) for _ in range(3))
+    gx, gy, gz = gpu.array(x), gpu.array(y), gpu.array(z)
+    hits0 = engine.stats.get("plan_hits", 0)
+    for a, b in ((1.5, 1.5), (2.0, -3.0), (0.25, 0.25), (1e300, 2.0), (-1.0, 7.0)):
+        assert_bits_equal((a * gx + b * gy).get(), a * x + b * y, f"a*x+b*y a={a} b={b}")
+        assert_bits_equal((a * gx + b * gx).get(), a * x + b * x, "same leaf twice")
+        assert_bits_equal((a * gz + b * gy).get(), a * z + b * y, "other leaves, same layout")
+    assert engine.stats.get("plan_hits", 0) > hits0 + 6
+    # float32 with guarded operations: the scalar's magnitude class is part of the plan
+    f = rng.uniform(0.5, 4.0, n).astype(np.float32)
+    gf = gpu.array(f)
+    for s in (0.3, 0.7, 1e-30, 3.0, 1e30, 0.3):
+        with np.errstate(all="ignore"):
+            assert_bits_equal((np.sqrt(gf) / (s * gf)).get(), (np.sqrt(f) / (np.float32(s) * f)), f"s={s}")
+    # layouts: slices (other offsets / strides), other sizes, in-place leaf astype
+    for sl in (slice(0, None), slice(1, None), slice(None, None, 2), slice(3, 1000)):
+        assert_bits_equal((1.5 * gx[sl] + gy[sl]).get(), 1.5 * x[sl] + y[sl], f"slice {sl}")
+    leaf = gpu.array(x)
+    assert_bits_equal((leaf * 2.0 + 1.0).get(), x * 2.0 + 1.0, "f64 leaf")
+    leaf.astype(np.float32)
+    assert_bits_equal((leaf * 2.0 + 1.0).get(), x.astype(np.float32) * np.float32(2.0) + np.float32(1.0),
+                      "same leaf after in-place astype")
+    # several roots in one kernel, replayed with a different sharing pattern between the roots
+    for a, b in ((2.0, 3.0), (2.0, 2.0), (5.0, 3.0)):
+        r1, r2 = a * gx + gy, b * gx - gy
+        gpu.evaluate(r1, r2)
+        assert_bits_equal(r1.get(), a * x + y, "root 1")
+        assert_bits_equal(r2.get(), b * x - y, "root 2")
+    # a materialised producer is reused (cut point), and mutation invalidates memoised results
+    d = gx * gy
+    d.run()
+    assert_bits_equal((d + 1.0).get(), x * y + 1.0, "materialised producer")
+    gx2 = gpu.array(x.copy())
+    r = gx2 * 3.0
+    assert_bits_equal(r.get(), x * 3.0, "before mutation")
+    gx2[0] = 100.0
+    xm = x.copy(); xm[0] = 100.0
+    assert_bits_equal((gx2 * 3.0).get(), xm * 3.0, "after mutation")
+
+
 # ------------------------------------------------------------------ C2: Black-Scholes
 def _bs_truth(S, K, T, r=0.02, v=0.30):
     S, K, T = (a.astype(np.float64) for a in (S, K, T))

@@ -160,6 +160,28 @@ def test_interval_analysis_places_guards(dry):
     assert ranges._mul(ranges.R(0, 100), ranges.R(0, 100)) is None, "may overflow: unknown"
 
 
+def test_plan_cache_skips_planning_on_replay(dry, monkeypatch):
+    """A second evaluation of the same expression STRUCTURE (new nodes, new scalar value) must
+    not plan again: engine.evaluate_nodes launches the prepared plan."""
+    x, y = dr.array(np.ones(1 << 12)), dr.array(np.ones(1 << 12))
+    (1.5 * x + y).run()
+    calls = []
+    real = planner.build_program
+    monkeypatch.setattr(planner, "build_program", lambda nodes: calls.append(1) or real(nodes))
+    n0 = len(dry)
+    (2.5 * x + y).run()
+    (1.5 * y + x).run()
+    assert calls == [] and len(dry) == n0 + 2
+    assert dry[-1][0] is dry[n0 - 1][0], "same kernel object"
+    (2.5 * x + x).run()                       # other sharing pattern: one operand -> planned
+    assert len(calls) == 1
+    (x[1:] * 2.5 + y[1:]).run()               # other layout (unaligned view) -> planned
+    assert len(calls) == 2
+    monkeypatch.setattr(engine, "_PLAN_CACHE", False)
+    (2.5 * x + y).run()
+    assert len(calls) == 3
+
+
 def test_cubin_is_sm100a_with_vector_ldst(dry, tmp_path):
     import subprocess
     x, y = dr.array(np.ones(1 << 12)), dr.array(np.ones(1 << 12))
