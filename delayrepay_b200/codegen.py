@@ -243,7 +243,13 @@ def gen_flat(name, prog, in_class, out_dts, vec_ok, stream, reduce=None, unroll=
                      and os.environ.get("DR_ERF_REP", "16") != "1") else 1
     if threads is None:
         threads = int(os.environ.get("DR_THREADS", 0)) or (1024 if erf_rep == 16 else 256)
-    NS = int(os.environ.get("DR_STAGES", 0)) or (2 if erf_rep == 16 else 3)
+    # vectors per lane per stage: a stage of VPL tiles is filled by ONE bulk copy per operand and
+    # consumed by VPL trips of the (not unrolled) inner loop, so the barrier wait, the tile
+    # arithmetic and the TMA issue are paid once per VPL vectors.  With the 84 KiB erf table the
+    # ring is a single 2-tile stage per warp (the refill overlaps the second vector's arithmetic
+    # and the other 31 warps hide the rest of the DRAM latency).
+    VPL = int(os.environ.get("DR_VPL", 0)) or 2
+    NS = int(os.environ.get("DR_STAGES", 0)) or (1 if erf_rep == 16 else 2)
 
     params = ["const i64 n"]
     for i, a in enumerate(arrays):
@@ -323,7 +329,7 @@ def gen_flat(name, prog, in_class, out_dts, vec_ok, stream, reduce=None, unroll=
 
     prefetch = (not staged) and U == 1 and body_weight(prog) >= 2 \
         and os.environ.get("DR_PREFETCH", "0") != "0"
-    ring_bytes = NS * len(c_inputs) * threads * 16 if staged else 0
+    ring_bytes = NS * VPL * len(c_inputs) * threads * 16 if staged else 0
     if meta is not None:
         meta["smem"] = ring_bytes + (3 * ERF2_ROWS * 16 * 8 if erf_rep == 16 else 0)
         meta["threads"] = threads
@@ -336,7 +342,8 @@ def gen_flat(name, prog, in_class, out_dts, vec_ok, stream, reduce=None, unroll=
         # in flight while one is evaluated, and no register is held for them.
         nin = len(c_inputs)
         WPB = threads // 32
-        SB = nin * 512                                   # bytes per stage
+        TB = 512 * VPL                                   # bytes per operand per stage
+        SB = nin * TB                                    # bytes per stage
         w("  extern __shared__ __align__(128) unsigned char dr_smem[];")
         if erf_rep == 16:
             w(f"  float2* const dr_erf_tab = reinterpret_cast<float2*>(dr_smem + {ring_bytes});")
@@ -351,29 +358,39 @@ def gen_flat(name, prog, in_class, out_dts, vec_ok, stream, reduce=None, unroll=
         w(f"  if (dr_lane == 0) {{ for (int s = 0; s < {NS}; ++s) dr_mbar_init(&dr_bar[dr_warp * {NS} + s], 1); dr_fence_barrier_init(); }}")
         w("  __syncwarp();")
         # tiles are counted in 32 bits: n / (32 * V) < 2^32 for any array that fits in HBM
-        w("  const unsigned ntiles = (unsigned)((nv + 31) / 32);")
-        w("  const unsigned dr_last_bytes = (unsigned)(nv - (i64)(ntiles - 1) * 32) * 16u;")
+        w(f"  const unsigned ntiles = (unsigned)((nv + {32 * VPL - 1}) / {32 * VPL});")
+        w(f"  const unsigned dr_last_bytes = (unsigned)(nv - (i64)(ntiles - 1) * {32 * VPL}) * 16u;")
         w(f"  const unsigned dr_gw = blockIdx.x * {WPB}u + dr_warp, dr_nw = gridDim.x * {WPB}u;")
-        w("  auto dr_issue = [&](unsigned tile, unsigned stage) {       // lane 0, tile < ntiles")
-        w("    const unsigned bytes = tile == ntiles - 1 ? dr_last_bytes : 512u;")
+        w("  auto dr_issue = [&](unsigned tile, unsigned stage) {       // one elected lane, tile < ntiles")
+        w(f"    const unsigned bytes = tile == ntiles - 1 ? dr_last_bytes : {TB}u;")
         w("    const unsigned bar = dr_bar_s + stage * 8u;")
         w(f"    const unsigned dst = dr_ring_s + stage * {SB}u;")
         w(f"    dr_mbar_expect_tx_s(bar, bytes * {nin}u);")
         for slot, (i, a) in enumerate(c_inputs):
-            w(f"    dr_bulk_load_s(dst + {slot * 512}u, in{i} + (i64)tile * {32 * V}, bytes, bar);")
+            w(f"    dr_bulk_load_s(dst + {slot * TB}u, in{i} + (i64)tile * {32 * VPL * V}, bytes, bar);")
         w("  };")
         w(f"  if (dr_lane == 0) {{ for (unsigned k = 0; k < {NS}u; ++k) if (dr_gw + k * dr_nw < ntiles) dr_issue(dr_gw + k * dr_nw, k); }}")
         w("  unsigned dr_stage = 0, dr_phase = 0;")
         w("  for (unsigned tile = dr_gw; tile < ntiles; tile += dr_nw) {")
         w("    dr_mbar_wait_s(dr_bar_s + dr_stage * 8u, dr_phase);")
-        w("    const i64 i = (i64)tile * 32 + dr_lane;")
-        w(f"    const unsigned dr_src = dr_ring_s + dr_stage * {SB}u + dr_lane * 16u;")
+        w("    const unsigned dr_cur = dr_stage;")
+        w(f"    if (++dr_stage == {NS}u) {{ dr_stage = 0; dr_phase ^= 1u; }}")
+        if VPL > 1:
+            w("#pragma unroll 1")
+            w(f"    for (unsigned dr_sub = 0; dr_sub < {VPL}u; ++dr_sub) {{")
+            w(f"    const i64 i = ((i64)tile * {VPL} + dr_sub) * 32 + dr_lane;")
+            w(f"    const unsigned dr_src = dr_ring_s + dr_cur * {SB}u + dr_sub * 512u + dr_lane * 16u;")
+        else:
+            w("    const i64 i = (i64)tile * 32 + dr_lane;")
+            w(f"    const unsigned dr_src = dr_ring_s + dr_cur * {SB}u + dr_lane * 16u;")
         for slot, (i, a) in enumerate(c_inputs):
             w(f"    Vec<{ctype(a.dtype)}, {V}> v{i}[1];")
-            w(f"    v{i}[0] = dr_lds16<{ctype(a.dtype)}, {V}>(dr_src + {slot * 512}u);")
-        w("    __syncwarp();             // every lane holds its vector: the stage can be refilled")
-        w(f"    if (tile + {NS}u * dr_nw < ntiles) {{ if (dr_elect()) dr_issue(tile + {NS}u * dr_nw, dr_stage); }}")
-        w(f"    if (++dr_stage == {NS}u) {{ dr_stage = 0; dr_phase ^= 1u; }}")
+            w(f"    v{i}[0] = dr_lds16<{ctype(a.dtype)}, {V}>(dr_src + {slot * TB}u);")
+        last = f"dr_sub == {VPL - 1}u && " if VPL > 1 else ""
+        w(f"    if ({last}true) {{")
+        w("      __syncwarp();           // every lane holds its last vector of the stage: refill it")
+        w(f"      if (tile + {NS}u * dr_nw < ntiles) {{ if (dr_elect()) dr_issue(tile + {NS}u * dr_nw, dr_cur); }}")
+        w("    }")
         w("    if (i < nv) {")
     elif prefetch:
         # software pipelining: the loads of the NEXT vector are in flight while this one is
@@ -459,6 +476,8 @@ def gen_flat(name, prog, in_class, out_dts, vec_ok, stream, reduce=None, unroll=
                 w(f"    v{i}[0] = nx{i};")
     if staged:
         w("    }")
+        if VPL > 1:
+            w("    }")
     w("  }")
     # scalar tail: the n - nv*V < V trailing elements, first threads of block 0, precise forms
     if V > 1:
