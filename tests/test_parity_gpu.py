@@ -268,6 +268,30 @@ def test_plan_cache_replays_are_exact(gpu):
     assert_bits_equal((gx2 * 3.0).get(), xm * 3.0, "after mutation")
 
 
+@pytest.mark.parametrize("n", [5, 63, 64, 65, 257, 4099, (1 << 18) + 7])
+def test_staged_kernels_all_dtypes_and_sizes(gpu, n):
+    """The per-warp TMA rings (two vectors per lane per stage) with partial stages, partial
+    vectors and scalar tails, for float32 (lockstep), float64 (two lanes per vector) and a fused
+    full reduction over a heavy body."""
+    rng = np.random.default_rng(n)
+    x = rng.uniform(0.5, 3.0, n)
+    y = rng.uniform(0.5, 3.0, n)
+    for dt, tol in ((np.float64, 4), (np.float32, 6)):
+        a, b = x.astype(dt), y.astype(dt)
+        got = (np.exp(gpu.array(a) * 0.5) * np.log(gpu.array(b)) / np.sqrt(gpu.array(a))).get()
+        want = np.exp(a * dt(0.5)) * np.log(b) / np.sqrt(a)
+        assert got.dtype == want.dtype
+        assert_ulp(got, want, tol, f"heavy chain {np.dtype(dt).name} n={n}")
+        s_got = float(np.sum(np.exp(gpu.array(a) * 0.5) * np.log(gpu.array(b))))
+        s_want = float(np.sum(np.exp(a.astype(np.float64) * 0.5) * np.log(b.astype(np.float64))))
+        rtol = 1e-12 if dt is np.float64 else 1e-5
+        assert abs(s_got - s_want) <= rtol * max(abs(s_want), np.abs(np.log(b)).sum() * 1e-3), (dt, n)
+    c, d = gpu.array(x.astype(np.float32)), gpu.array(y.astype(np.float32))
+    got = erf(c - 1.5) * np.exp(-d)
+    np.testing.assert_allclose(got.get(), erf(x.astype(np.float32) - np.float32(1.5)) * np.exp(-y.astype(np.float32)),
+                               rtol=1e-6, atol=1e-7)
+
+
 # ------------------------------------------------------------------ C2: Black-Scholes
 def _bs_truth(S, K, T, r=0.02, v=0.30):
     S, K, T = (a.astype(np.float64) for a in (S, K, T))
