@@ -836,7 +836,7 @@ def gen_cols(name, prog, in_class, reduce, threads=256):
 
 
 # --------------------------------------------------------------------------- stencil family
-def gen_stencil(name, prog, roles, out_dt, TW=248, TH=32, NS=4, threads=496):
+def gen_stencil(name, prog, roles, out_dt, TW=248, TH=32, NS=4, threads=992):
     """Shifted-view stencil over ONE 2-d base array, written to a fresh copy of the base
     (ping-pong: Jacobi semantics without the reference's temporary + copy, delayarray.py:114-121).
 

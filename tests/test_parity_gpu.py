@@ -386,7 +386,8 @@ def test_axis_reductions(gpu):
 
 
 # ------------------------------------------------------------------ C4: heat stencil, bit-exact
-@pytest.mark.parametrize("shape,steps", [((64, 64), 5), ((130, 257), 7), ((3, 3), 2), ((1000, 1031), 3)])
+@pytest.mark.parametrize("shape,steps", [((64, 64), 5), ((130, 257), 7), ((3, 3), 2), ((1000, 1031), 3),
+                                         ((2100, 4100), 3), ((4096, 8192), 2)])
 def test_heat_bit_exact(gpu, shape, steps):
     rng = np.random.default_rng(4)
     u0 = rng.random(shape, dtype=np.float32) if shape != (64, 64) else wl.make_inputs("heat", 64)["u"]
