@@ -764,7 +764,7 @@ def _try_mm_skinny(node, pa, m, k, n, res_dt, with_rowsum=None):
     kchunk = -(-kchunk // 256) * 256
     ksplit = -(-k // kchunk)
     pow_modes = codegen.relaxed_pow_modes(pa)
-    R, TH = 4, 128
+    R, TH = int(os.environ.get("DR_SK_R", 8)), int(os.environ.get("DR_SK_TH", 64))
     key = ("mm_skinny", pa.key(), tuple(roles), res_dt.str, n_out, tuple(sorted(pow_modes.items())), R, TH)
     kern = get_kernel(key, lambda name: codegen.gen_mm_skinny(
         name, pa, roles, res_dt, n_out, threads=TH, rows=R, pow_modes=pow_modes))
