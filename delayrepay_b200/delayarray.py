@@ -97,6 +97,7 @@ def reset():
     try:
         from . import engine
         engine._plans.clear()
+        engine._st_plans.clear()
     except ImportError:
         pass
 

@@ -199,9 +199,41 @@ class DeviceArray:
         base = np.empty(1, dtype=self.dtype)
         return base, np.lib.stride_tricks.as_strided(base, self.shape, self.strides)
 
+    def _basic_view(self, key):
+        """Fast path for a tuple of slices / ints (no Ellipsis, newaxis or negative steps
+        handled elsewhere): plain stride arithmetic, no NumPy shadow.  None = not applicable."""
+        if len(key) > len(self.shape):
+            return None
+        off = self.offset
+        shape, strides = [], []
+        for k, n, st in zip(key, self.shape, self.strides):
+            if type(k) is slice:
+                start, stop, step = k.indices(n)
+                if step <= 0:
+                    return None
+                cnt = (stop - start + step - 1) // step if stop > start else 0
+                off += start * st
+                shape.append(cnt)
+                strides.append(st * step)
+            elif type(k) is int:
+                if k < 0:
+                    k += n
+                if not 0 <= k < n:
+                    return None                 # let NumPy raise its IndexError
+                off += k * st
+            else:
+                return None
+        nk = len(key)
+        shape.extend(self.shape[nk:])
+        strides.extend(self.strides[nk:])
+        return DeviceArray(self.buf, tuple(shape), self.dtype, tuple(strides), off)
+
     def __getitem__(self, key):
         if isinstance(key, DeviceArray):
             raise NotImplementedError("advanced (array) indexing is not supported on device arrays")
+        fast = self._basic_view(key if type(key) is tuple else (key,))
+        if fast is not None:
+            return fast
         if isinstance(key, tuple) and any(isinstance(k, (np.ndarray, list, DeviceArray)) for k in key) \
                 or isinstance(key, (np.ndarray, list)):
             raise NotImplementedError("advanced (array) indexing is not supported on device arrays")

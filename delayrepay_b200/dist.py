@@ -116,6 +116,18 @@ class NcclComm:
         from .device import synchronize
         synchronize(self.dev)
 
+    def group(self):
+        """Context manager: the send/recv pairs issued inside become ONE NCCL launch."""
+        comm = self
+
+        class _Group:
+            def __enter__(self):
+                comm.check(comm.lib.drc_nccl_group_start())
+
+            def __exit__(self, *exc):
+                comm.check(comm.lib.drc_nccl_group_end())
+        return _Group()
+
     def close(self):
         if getattr(self, "comm", 0):
             self.lib.drc_nccl_destroy(self.comm)
@@ -153,8 +165,16 @@ def exchange_halos(u, comm, getrow, setrow):
     the same code drives device blocks (NcclComm) and host blocks (GlooComm)."""
     up, down, _ = halo_rows(comm.rank, comm.world, 0)
     n = u.shape[0]
-    # phase 1: send my first interior row up, receive my down halo from below
     first, last = (1 if up else 0), (n - 2 if down else n - 1)
+    if isinstance(comm, NcclComm):
+        # both directions in one NCCL group: one launch per step, receives land in the halo rows
+        with comm.group():
+            comm.sendrecv(getrow(u, first) if up else None, comm.rank - 1 if up else -1,
+                          getrow(u, n - 1) if down else None, comm.rank + 1 if down else -1)
+            comm.sendrecv(getrow(u, last) if down else None, comm.rank + 1 if down else -1,
+                          getrow(u, 0) if up else None, comm.rank - 1 if up else -1)
+        return u
+    # phase 1: send my first interior row up, receive my down halo from below
     got = comm.sendrecv(getrow(u, first) if up else None, comm.rank - 1 if up else -1,
                         getrow(u, n - 1) if down else None, comm.rank + 1 if down else -1)
     if down:

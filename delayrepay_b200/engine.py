@@ -837,6 +837,14 @@ def assign(target, value):
                              f"into shape {target.shape}")
     if target.size == 0:
         return
+    st_key = st_ops = None
+    if _PLAN_CACHE and src.kind == "ewise" and src.__dict__.get("_psig") is not None:
+        st_key, st_ops = _stencil_plan_key(src, target)
+        if st_key is not None:
+            plan = _st_plans.get(st_key)
+            if plan is not None and _stencil_plan_launch(plan, st_ops, target):
+                target.buf.version += 1
+                return
     prog = planner.build_program([src]) if src.kind != "scalar" else _scalar_program(src)
     prog.shape = tuple(target.shape)
     tkey = (target.offset, planner.broadcast_strides(target, target.shape))
@@ -848,7 +856,7 @@ def assign(target, value):
                 inplace = True
             else:
                 hazard = True
-    if hazard and _try_stencil(prog, target):
+    if hazard and _try_stencil(prog, target, st_key, st_ops):
         target.buf.version += 1
         return
     if hazard:
@@ -881,7 +889,64 @@ def encode_tensormap(dev, dtype_name, gptr, dims, strides_bytes, box, swizzle=0,
     return bytes(raw[off:off + 128])
 
 
-def _try_stencil(prog, target):
+# Prepared stencil launches (the assignment counterpart of _plans): keyed on the RHS signature,
+# the target view and, for every leaf that aliases the target's buffer, its exact offset (the
+# shift).  A replay allocates the ping-pong buffer, reuses the tensor map encoded for the current
+# base address (two addresses alternate) and launches; no planning, no role analysis.
+_st_plans = {}
+
+
+class _StPlan:
+    __slots__ = ("kern", "meta", "geo", "grid", "arr_idx", "leaf_sigs", "sc_idx", "sc_dt", "tmaps",
+                 "cols", "rows", "pitch")
+
+
+def _stencil_plan_key(src, target):
+    ops = src._pops
+    tb = target.buf
+    lk = []
+    for o in ops:
+        if o.kind == "leaf":
+            arr = o.array
+            if not isinstance(arr, DeviceArray):
+                return None, None
+            lk.append(arr.offset if arr.buf is tb else -1)
+    return (src._psig, src.shape, target.offset, target.shape, target.strides, target.dtype.str,
+            tb.nbytes, tuple(lk), target.dev), ops
+
+
+def _stencil_plan_launch(plan, ops, target):
+    from .delayarray import _leaf_sig
+    arrays = []
+    for i, want in zip(plan.arr_idx, plan.leaf_sigs):
+        leaf = ops[i]
+        if _leaf_sig(leaf) != want:
+            return False
+        arrays.append(leaf._force())
+    buf, dev, m = target.buf, target.dev, plan.meta
+    out = DeviceBuffer(buf.nbytes, dev) if dev >= 0 else DeviceBuffer(buf.nbytes)
+    tmap = plan.tmaps.get(buf.ptr)
+    if tmap is None:
+        if len(plan.tmaps) >= 8:
+            plan.tmaps.clear()
+        tmap = plan.tmaps[buf.ptr] = encode_tensormap(
+            dev, target.dtype.name, buf.ptr, (plan.cols, plan.rows), (plan.pitch,), (m["BW"], m["BH"]))
+    a = Args()
+    a.raw(tmap, 64)
+    a.raw(plan.geo, 8)
+    a.ptr(buf.ptr)
+    a.ptr(out.ptr)
+    for arr in arrays:
+        a.ptr(arr.ptr)
+    for i, dt in zip(plan.sc_idx, plan.sc_dt):
+        a.scalar(ops[i].val, dt)
+    launch(plan.kern, dev, plan.grid, m["threads"], a, smem=m["smem"])
+    buf.swap_storage(out)
+    stats["plan_hits"] = stats.get("plan_hits", 0) + 1
+    return True
+
+
+def _try_stencil(prog, target, plan_key=None, plan_ops=None):
     """Shifted-view self-assignment on a 2-d base array -> TMA-staged stencil kernel writing a
     fresh copy of the base, then the two allocations are swapped (ping-pong).  Returns False
     when the pattern does not apply (the caller falls back to temporary + copy)."""
@@ -962,8 +1027,41 @@ def _try_stencil(prog, target):
         per_sm = min(per_sm, kern.blocks_per_sm(dev, m["threads"], m["smem"]))
     grid = min(tiles_x * tiles_y, st.sm_count * per_sm)
     launch(kern, dev, grid, m["threads"], a, smem=m["smem"])
+    if plan_key is not None:
+        _stencil_plan_record(plan_key, plan_ops, prog, kern, geo, grid, cols, rows, pitch)
     buf.swap_storage(out)              # `out` now owns the old allocation and frees it (stream-ordered)
     return True
+
+
+def _stencil_plan_record(key, ops, prog, kern, geo, grid, cols, rows, pitch):
+    from .delayarray import _leaf_sig
+    arr_idx, leaf_sigs, sc_idx = [], [], []
+    for arr in prog.arrays:
+        for i, o in enumerate(ops):
+            if o.kind == "leaf" and o._force() is arr:
+                sig = _leaf_sig(o)
+                if sig is None:
+                    return
+                arr_idx.append(i)
+                leaf_sigs.append(sig)
+                break
+        else:
+            return
+    for node in prog.scalar_nodes:
+        for i, o in enumerate(ops):
+            if o is node:
+                sc_idx.append(i)
+                break
+        else:
+            return
+    if len(_st_plans) >= _PLAN_LIMIT:
+        _st_plans.clear()
+    p = _StPlan()
+    p.kern, p.meta, p.geo, p.grid = kern, kern.meta, geo, grid
+    p.arr_idx, p.leaf_sigs, p.sc_idx = tuple(arr_idx), tuple(leaf_sigs), tuple(sc_idx)
+    p.sc_dt = tuple(dt for _, dt in prog.scalars)
+    p.tmaps, p.cols, p.rows, p.pitch = {}, cols, rows, pitch
+    _st_plans[key] = p
 
 
 def _scalar_program(node):
