@@ -210,6 +210,26 @@ class DelayArray(numpy.lib.mixins.NDArrayOperatorsMixin):
             return MVEx(transpose(right), left)
         raise NotImplementedError(f"dot of shapes {left.shape} and {right.shape}")
 
+    # ---- arithmetic operators: straight to capture.  NDArrayOperatorsMixin would route
+    # `a + b` through np.add's override machinery and back into __array_ufunc__ (~4 us per
+    # operator on the capture path); the result is the same node either way.
+    def _binop(ufunc, swap=False):                                   # noqa: N805
+        def op(self, other):
+            if swap:
+                return create_ex(ufunc, [arg_to_numpy_ex(other), self])
+            return create_ex(ufunc, [self, arg_to_numpy_ex(other)])
+        return op
+
+    __add__, __radd__ = _binop(np.add), _binop(np.add, True)
+    __sub__, __rsub__ = _binop(np.subtract), _binop(np.subtract, True)
+    __mul__, __rmul__ = _binop(np.multiply), _binop(np.multiply, True)
+    __truediv__, __rtruediv__ = _binop(np.true_divide), _binop(np.true_divide, True)
+    __pow__, __rpow__ = _binop(np.power), _binop(np.power, True)
+    del _binop
+
+    def __neg__(self):
+        return create_ex(np.negative, [self])
+
     def __matmul__(self, other):
         return self._dot([self, other])
 
