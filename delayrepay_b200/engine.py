@@ -70,11 +70,25 @@ def kernel_name(key):
     return f"dr_{family}_" + hashlib.sha256(repr(key).encode()).hexdigest()[:16]
 
 
+_NVRTC_TAG = []
+
+
+def _nvrtc_tag():
+    """'nvrtc-12.9': part of the cubin cache key (code generation differs between releases)."""
+    if not _NVRTC_TAG:
+        try:
+            ma, mi, _ = _lib.nvrtc_version()
+            _NVRTC_TAG.append(f"nvrtc-{ma}.{mi}")
+        except Exception:
+            _NVRTC_TAG.append("nvrtc-?")
+    return _NVRTC_TAG[0]
+
+
 def compile_source(name, body_source):
     """Source text -> cubin through the on-disk cache (works without a GPU)."""
     import time
     source = PRELUDE + "\n" + body_source
-    digest = hashlib.sha256((source + "\0" + " ".join(NVRTC_OPTIONS)).encode()).hexdigest()
+    digest = hashlib.sha256((source + "\0" + " ".join(NVRTC_OPTIONS) + "\0" + _nvrtc_tag()).encode()).hexdigest()
     path = os.path.join(CACHE_DIR, f"{name}-{digest[:16]}.cubin")
     if os.path.exists(path):
         with open(path, "rb") as f:
