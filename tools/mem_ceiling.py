@@ -42,3 +42,6 @@ for name, fn, bytes_per in (("3 in / 2 out, adds only", light, 20), ("3 in / 1 o
                             ("1 in / 1 out (copy-like)", copy1, 8)):
     ms = timed(fn)
     print(f"{name:28s} {ms:7.3f} ms  {n * bytes_per / ms / 1e6:7.0f} GB/s")
+# the same pattern sustained (power-capped regime): 200 back-to-back launches
+ms = timed(light, 200)
+print(f"{'3 in / 2 out, 200 launches':28s} {ms:7.3f} ms  {n * 20 / ms / 1e6:7.0f} GB/s")
