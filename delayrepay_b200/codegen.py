@@ -237,18 +237,21 @@ def gen_flat(name, prog, in_class, out_dts, vec_ok, stream, reduce=None, unroll=
     staged = (U == 1 and V > 1 and body_weight(prog) >= 2 and c_inputs
               and all(a.dtype.itemsize * V == 16 for _, a in c_inputs)
               and os.environ.get("DR_STAGED", "1") != "0")
-    # table-driven erf in a staged kernel: ONE 1024-thread CTA per SM, so that 16 bank-private
-    # replicas of the table (84 KiB) fit beside the per-warp operand rings
+    # table-driven erf in a staged kernel: ONE CTA per SM, so that 16 bank-private replicas of
+    # the table (84 KiB) fit beside the per-warp operand rings.  512 threads with four vectors
+    # per lane per stage: the kernel no longer depends on occupancy (same time at 512 .. 1024
+    # threads) and with 128 registers available the compiler stops re-materialising constants
+    # (422 instead of 448 instructions per vector), which matters under the power cap.
     erf_rep = 16 if (staged and lockstep and GEN2 and uses_erf_table(prog)
                      and os.environ.get("DR_ERF_REP", "16") != "1") else 1
     if threads is None:
-        threads = int(os.environ.get("DR_THREADS", 0)) or (1024 if erf_rep == 16 else 256)
+        threads = int(os.environ.get("DR_THREADS", 0)) or (512 if erf_rep == 16 else 256)
     # vectors per lane per stage: a stage of VPL tiles is filled by ONE bulk copy per operand and
     # consumed by VPL trips of the (not unrolled) inner loop, so the barrier wait, the tile
     # arithmetic and the TMA issue are paid once per VPL vectors.  With the 84 KiB erf table the
-    # ring is a single 2-tile stage per warp (the refill overlaps the second vector's arithmetic
-    # and the other 31 warps hide the rest of the DRAM latency).
-    VPL = int(os.environ.get("DR_VPL", 0)) or 2
+    # ring is a single 4-tile stage per warp (the refill overlaps the last vector's arithmetic
+    # and the other warps hide the rest of the DRAM latency).
+    VPL = int(os.environ.get("DR_VPL", 0)) or (4 if erf_rep == 16 else 2)
     NS = int(os.environ.get("DR_STAGES", 0)) or (1 if erf_rep == 16 else 2)
 
     params = ["const i64 n"]
@@ -290,7 +293,7 @@ def gen_flat(name, prog, in_class, out_dts, vec_ok, stream, reduce=None, unroll=
         w("  return res;")
         w("}")
     min_blocks = min_blocks or int(os.environ.get("DR_MINBLOCKS", 0)) or (
-        (1024 // threads) if (lockstep and body_weight(prog) >= 2) else None)   # 64 registers
+        (1 if erf_rep == 16 else 1024 // threads) if (lockstep and body_weight(prog) >= 2) else None)
     lb = f"__launch_bounds__({threads}" + (f", {min_blocks})" if min_blocks else ")")
     w(f'extern "C" __global__ void {lb} {name}({", ".join(params)}) {{')
     for i, (a, c) in enumerate(zip(arrays, in_class)):
@@ -616,7 +619,8 @@ def emit_body_lockstep(prog, in_class, V=4, sclasses=None, erf_rep=1):
             if op == "multiply":
                 packed_products.add(me)
         elif same and an is not None and op in _LANE4_R and k in an.check:
-            flags = ", ".join("true" if c else "false" for c in an.check[k])
+            flags = ", ".join(("true" if c else "false") if isinstance(c, bool) else str(int(c))
+                              for c in an.check[k])
             if op == "erf":
                 flags += f", {erf_rep}"
             extra = _TABLE_ARG.get(_LANE4_R[op], "")

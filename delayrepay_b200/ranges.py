@@ -222,7 +222,9 @@ def analyse(prog, in_class, sclasses, guarded_ops):
                 val[me] = None
         elif op == "exp":
             r = a[0]
-            c = r is None or r.hi > 6                  # |x| < 64 < 87
+            # 0: |x| <= 64 proven; 1: nothing known (per-lane test, nan included);
+            # 2: finite and not nan, magnitude unknown (one test on the lanes' max |x|)
+            c = 1 if r is None else (2 if r.hi > 6 else 0)
             if op in guarded_ops:
                 out.check[k] = (c,)
                 val[me] = R(MIN_NORM, MAX_EXP, neg=False)
