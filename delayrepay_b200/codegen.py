@@ -680,9 +680,16 @@ def _emit_reduce_finish(w, rop, acc_dt, res_dt, U):
 
 
 # --------------------------------------------------------------------------- nd family
-def gen_nd(name, prog, ndim, in_class, out_dts, reduce=None, threads=256, wide_index=False):
+def gen_nd(name, prog, ndim, in_class, out_dts, reduce=None, threads=256, wide_index=False, vec=0,
+           sclasses=None):
     """General strided/broadcast kernel.  Geometry arrives in one struct argument:
-    shape[ndim], then byte strides per operand per dim (inputs then outputs)."""
+    shape[ndim], then byte strides per operand per dim (inputs then outputs).
+    ``vec`` = V > 1: the innermost dimension is walked in vectors of V elements (planner.
+    _try_inner_vectors): operands of class 'v' are read with one 128-bit load, class 'i' (no
+    movement along the inner dimension) with one scalar load shared by the V lanes, outputs are
+    written with one 128-bit store; the index decomposition is paid once per V elements."""
+    if vec and vec > 1 and reduce is None:
+        return _gen_nd_vec(name, prog, ndim, in_class, out_dts, vec, threads, wide_index, sclasses)
     arrays, scalars = prog.arrays, prog.scalars
     n_ops = len(arrays) + (len(out_dts) if reduce is None else 0)
     I = "i64" if wide_index else "u32"
@@ -735,6 +742,92 @@ def gen_nd(name, prog, ndim, in_class, out_dts, reduce=None, threads=256, wide_i
     w("  }")
     if reduce is not None:
         _emit_reduce_finish(w, rop, acc_dt, res_dt, 1)
+    w("}")
+    return "\n".join(src) + "\n"
+
+
+def _gen_nd_vec(name, prog, ndim, in_class, out_dts, V, threads, wide_index, sclasses=None):
+    arrays, scalars = prog.arrays, prog.scalars
+    n_ops = len(arrays) + len(out_dts)
+    I = "i64" if wide_index else "u32"
+    src = []
+    w = src.append
+    w(f"struct Geo_{name} {{ i64 total; i64 shape[{ndim}]; i64 stride[{max(n_ops, 1)}][{ndim}]; }};")
+    params = [f"const Geo_{name} g"]
+    for i, a in enumerate(arrays):
+        params.append(f"const char* __restrict__ in{i}")
+    for j, (_, dt) in enumerate(scalars):
+        params.append(f"const {ctype(dt)} s{j}")
+    for o, dt in enumerate(out_dts):
+        params.append(f"char* __restrict__ out{o}")
+    body = emit_body(prog)
+    # float32 vectors of four: the lockstep body of the flat family (packed f32x2 arithmetic,
+    # branch-free guarded / sqrt log exp erf, precise re-evaluation of a flagged vector)
+    f32 = all(a.dtype == F32 for a in arrays) and all(np.dtype(d) == F32 for d in out_dts)
+    lock = V == 4 and f32 and os.environ.get("DR_LOCKSTEP", "1") != "0"
+    if lock:
+        lane_class = tuple("c" if c == "v" else "b" for c in in_class)
+        lock_body, lock_uniform = emit_body_lockstep(prog, lane_class, V, sclasses, 1)
+    w(f'extern "C" __global__ void __launch_bounds__({threads}) {name}({", ".join(params)}) {{')
+    if lock:
+        emit_explog_stage(w, prog)
+        if uses_erf_table(prog):
+            if GEN2:
+                w("  __shared__ float2 dr_erf_tab[3 * DR_ERF2_ROWS];")
+                w("  dr_erf2_tab_stage<1>(dr_erf_tab);")
+            else:
+                w("  __shared__ float2 dr_erf_tab[DR_ERF_TAB_PAIRS];")
+                w("  dr_erf_tab_stage(dr_erf_tab);")
+        w(DR_ONE.format("g.total"))
+    for i, (a, c) in enumerate(zip(arrays, in_class)):
+        if c == "b":
+            w(f"  const {ctype(a.dtype)} x{i} = *reinterpret_cast<const {ctype(a.dtype)}*>(in{i});")
+    w(f"  const {I} total = ({I})g.total;")
+    w(f"  const {I} step = ({I})gridDim.x * blockDim.x;")
+    w(f"  for ({I} idx = ({I})blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += step) {{")
+    w(f"    {I} rem = idx;")
+    w(f"    i64 off[{max(n_ops, 1)}];")
+    w(f"#pragma unroll\n    for (int k = 0; k < {max(n_ops, 1)}; ++k) off[k] = 0;")
+    w(f"#pragma unroll\n    for (int d = {ndim - 1}; d >= 0; --d) {{")
+    w(f"      const {I} extent = ({I})g.shape[d];")
+    w(f"      const {I} q = d ? rem / extent : 0;")
+    w(f"      const {I} c = d ? rem - q * extent : rem;")
+    w("      rem = q;")
+    w(f"#pragma unroll\n      for (int k = 0; k < {max(n_ops, 1)}; ++k) off[k] += (i64)c * g.stride[k][d];")
+    w("    }")
+    for i, (a, c) in enumerate(zip(arrays, in_class)):
+        T = ctype(a.dtype)
+        if c == "v":
+            w(f"    Vec<{T}, {V}> v{i}[1];")
+            w(f"    v{i}[0] = dr_ld<false, {T}, {V}>(reinterpret_cast<const {T}*>(in{i} + off[{i}]));")
+        elif c == "i":
+            w(f"    const {T} x{i} = *reinterpret_cast<const {T}*>(in{i} + off[{i}]);")
+    for o, dt in enumerate(out_dts):
+        w(f"    Vec<{ctype(dt)}, {V}> r{o};")
+    if lock:
+        w("    constexpr int u = 0;")
+        w("    bool bad = false;")
+        for line in lock_body:
+            w(f"    {line}")
+        w(f"#pragma unroll\n    for (int e = 0; e < {V}; ++e) {{")
+        for o, (r, dt) in enumerate(zip(prog.roots, out_dts)):
+            w(f"      r{o}.v[e] = {_lane_store(prog, r, dt, lane_class, lock_uniform)};")
+        w("    }")
+        w("    if (bad) {                                   // rare: precise re-evaluation")
+    w(f"#pragma unroll\n    for (int e = 0; e < {V}; ++e) {{")
+    for i, (a, c) in enumerate(zip(arrays, in_class)):
+        if c == "v":
+            w(f"      const {ctype(a.dtype)} x{i} = v{i}[0].v[e];")
+    for line in body:
+        w(f"      {line}")
+    for o, (r, dt) in enumerate(zip(prog.roots, out_dts)):
+        w(f"      r{o}.v[e] = {_store_expr(prog, r, dt)};")
+    w("    }")
+    if lock:
+        w("    }")
+    for o, dt in enumerate(out_dts):
+        w(f"    dr_st<false, {ctype(dt)}, {V}>(reinterpret_cast<{ctype(dt)}*>(out{o} + off[{len(arrays) + o}]), r{o});")
+    w("  }")
     w("}")
     return "\n".join(src) + "\n"
 

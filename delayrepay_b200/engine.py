@@ -295,7 +295,7 @@ def run_program(prog, outs, reduce=None, inplace=False):
     [] with ``reduce`` = (op, acc_dt, res_dt, count, result DeviceArray) for a full reduction."""
     dev = outs[0].dev if outs else (prog.arrays[0].dev if prog.arrays else current_device())
     st = dev_state(dev)
-    lay = planner.resolve_layout(prog, outs)
+    lay = planner.resolve_layout(prog, outs, inner_vectors=reduce is None and not os.environ.get("DR_NO_NDVEC"))
     if lay.total == 0:
         return
     out_dts = tuple(o.dtype for o in outs)
@@ -338,11 +338,14 @@ def run_program(prog, outs, reduce=None, inplace=False):
         threads = 256
         wide = lay.total >= (1 << 32) or any(
             abs(s) * n >= (1 << 62) for stv in lay.in_strides for s, n in zip(stv, lay.shape))
+        vec = int(lay.vec_ok) if (lay.vec_ok and reduce is None) else 0
+        scl = ranges.scalar_classes(prog) if (vec == 4 and codegen.has_lane_fast(prog)) else None
         key = ("nd", prog.key(), len(lay.shape), lay.in_class, tuple(d.str for d in out_dts),
-               red_key, wide)
+               red_key, wide, vec, scl)
         gen_reduce = None if reduce is None else (reduce[0], reduce[1], reduce[2], None)
         kern = get_kernel(key, lambda name: codegen.gen_nd(
-            name, prog, len(lay.shape), lay.in_class, out_dts, gen_reduce, wide_index=wide))
+            name, prog, len(lay.shape), lay.in_class, out_dts, gen_reduce, wide_index=wide, vec=vec,
+            sclasses=scl))
         a = Args()
         operands = list(lay.in_strides) + (list(lay.out_strides) if reduce is None else [])
         if not operands:
@@ -363,7 +366,7 @@ def run_program(prog, outs, reduce=None, inplace=False):
         a.ptr(reduce[4].ptr)
         a.f64(reduce[3])
     launch(kern, dev, grid, threads, a, smem=smem)
-    return kern, grid, threads, smem, head, (scl if lay.family == "flat" else None)
+    return kern, grid, threads, smem, head, scl
 
 
 # --------------------------------------------------------------------------- prepared launches

@@ -238,7 +238,7 @@ class Layout:
         return (self.family, len(self.shape), self.in_class, self.vec_ok)
 
 
-def resolve_layout(prog, outs):
+def resolve_layout(prog, outs, inner_vectors=True):
     """Pick the kernel family for program ``prog`` writing into DeviceArrays ``outs``."""
     shape = prog.shape
     # fast path: every operand is a C-contiguous array of exactly the iteration shape
@@ -289,4 +289,44 @@ def resolve_layout(prog, outs):
         lay.family = "nd"
         lay.in_class = tuple("b" if all(s == 0 for s in st) else "s" for st in lay.in_strides)
         lay.vec_ok = False
+        if inner_vectors and outs:
+            _try_inner_vectors(prog, outs, lay)
     return lay
+
+
+def _try_inner_vectors(prog, outs, lay):
+    """nd family with 128-bit accesses along the innermost collapsed dimension: every operand is
+    either contiguous along it ('v': stride == itemsize, vector load/store) or does not move along
+    it ('i': stride 0, one scalar load reused by the vector's lanes; 'b' stays a kernel-wide
+    scalar).  Needs equal-width element types, an inner extent that is a multiple of the vector
+    length and 16-byte aligned bases and outer strides.  Rewrites lay in place (vec_ok = V)."""
+    sizes = {a.dtype.itemsize for a in prog.arrays} | {o.dtype.itemsize for o in outs}
+    if len(sizes) != 1:
+        return
+    item = sizes.pop()
+    V = 16 // item
+    if V < 2 or lay.shape[-1] % V or lay.total >= (1 << 32):
+        return
+    cls = []
+    for a, st, c in zip(prog.arrays, lay.in_strides, lay.in_class):
+        if c == "b":
+            cls.append("b")
+        elif st[-1] == item:
+            if a.ptr % 16 or any(x % 16 for x in st[:-1]):
+                return
+            cls.append("v")
+        elif st[-1] == 0:
+            cls.append("i")
+        else:
+            return
+    for o, st in zip(outs, lay.out_strides):
+        if st[-1] != item or o.ptr % 16 or any(x % 16 for x in st[:-1]):
+            return
+    if "v" not in cls and not outs:
+        return
+    lay.in_class = tuple(cls)
+    lay.vec_ok = V
+    lay.shape = lay.shape[:-1] + (lay.shape[-1] // V,)
+    lay.total //= V
+    lay.in_strides = [st[:-1] + (st[-1] * V,) for st in lay.in_strides]
+    lay.out_strides = [st[:-1] + (st[-1] * V,) for st in lay.out_strides]

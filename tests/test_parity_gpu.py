@@ -292,6 +292,40 @@ def test_staged_kernels_all_dtypes_and_sizes(gpu, n):
                                rtol=1e-6, atol=1e-7)
 
 
+def test_nd_kernels_with_inner_vectors_bit_exact(gpu):
+    """Strided / broadcast regions whose innermost dimension is contiguous are walked in 128-bit
+    vectors (planner._try_inner_vectors); everything else stays on the scalar nd kernel.  Both
+    must agree with NumPy bit for bit."""
+    rng = np.random.default_rng(31)
+    for dt in (np.float32, np.float64):
+        X = rng.standard_normal((257, 1024)).astype(dt)
+        mu = rng.standard_normal(1024).astype(dt)
+        sd = rng.uniform(0.5, 2.0, 257).astype(dt)
+        gX, gmu, gsd = gpu.array(X), gpu.array(mu), gpu.array(sd)
+        assert_bits_equal(((gX - gmu[None, :]) / gsd[:, None]).get(), (X - mu[None, :]) / sd[:, None],
+                          f"row and column broadcast {np.dtype(dt).name}")
+        assert_bits_equal((gX[1:-1, 4:-4] * 2.0 + gX[2:, 4:-4]).get(), X[1:-1, 4:-4] * 2.0 + X[2:, 4:-4],
+                          "aligned strided views")
+        assert_bits_equal((gX[1:-1, 1:-3] * 2.0 + gX[2:, 3:-1]).get(), X[1:-1, 1:-3] * 2.0 + X[2:, 3:-1],
+                          "misaligned views (scalar nd)")
+        assert_bits_equal((gX[:, ::2] + 1.0).get(), X[:, ::2] + 1.0, "strided inner (scalar nd)")
+        assert_bits_equal((gX.T * 3.0).get(), X.T * 3.0, "transposed (scalar nd)")
+        assert_bits_equal((gX[:, :1022] - gmu[None, :1022]).get(), X[:, :1022] - mu[None, :1022],
+                          "inner extent not a multiple of 4 for f32")
+        a, b = gX[:200, :512] + gmu[None, :512], gX[:200, 512:] * gsd[:200, None]
+        gpu.evaluate(a, b)
+        assert_bits_equal(a.get(), X[:200, :512] + mu[None, :512], "two outputs, first")
+        assert_bits_equal(b.get(), X[:200, 512:] * sd[:200, None], "two outputs, second")
+        T3 = rng.standard_normal((6, 33, 64)).astype(dt)
+        g3 = gpu.array(T3)
+        assert_bits_equal((g3 * gpu.array(mu[:64])[None, None, :] + g3[:, :1, :]).get(),
+                          T3 * mu[:64][None, None, :] + T3[:, :1, :], "3-d with a broadcast middle axis")
+    Xi = rng.integers(-100, 100, (64, 256)).astype(np.int32)
+    assert_bits_equal((gpu.array(Xi) + gpu.array(Xi[0])[None, :]).get(), Xi + Xi[0][None, :], "int32")
+    assert_bits_equal((gpu.array(X.astype(np.float32)) + gpu.array(sd)[:, None]).get(),
+                      X.astype(np.float32) + sd[:, None], "mixed widths (scalar nd)")
+
+
 # ------------------------------------------------------------------ C2: Black-Scholes
 def _bs_truth(S, K, T, r=0.02, v=0.30):
     S, K, T = (a.astype(np.float64) for a in (S, K, T))
