@@ -201,7 +201,7 @@ def main():
     ap.add_argument("--cpu-log2n", type=int, default=24, help="CPU baseline sample size")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e-log2chunk", type=int, default=26)
+    ap.add_argument("--e2e-log2chunk", type=int, default=25)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--others", action="store_true", help="also time configs 1, 3, 4, 5 (N=1)")
     args = ap.parse_args()
