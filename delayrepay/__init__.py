@@ -11,3 +11,7 @@ _sys.modules[__name__ + ".delayarray"] = _impl.delayarray
 _sys.modules[__name__ + ".backend"] = _impl.backend
 _sys.modules[__name__ + ".random"] = _impl.random
 _sys.modules[__name__ + ".fft"] = _impl.fft
+
+
+def __getattr__(name):
+    return getattr(_impl, name)         # NumPy pass-through for everything else (see _impl)

@@ -13,4 +13,18 @@ from . import random, fft                   # noqa: F401
 from .stream import map_chunks              # noqa: F401
 
 pi = backend.backend.np.pi
+
+
+def __getattr__(name):
+    """Names this module does not define resolve to NumPy's (constants, dtypes, every ufunc and
+    array function): called with a DelayArray they dispatch into the engine through
+    __array_ufunc__ / __array_function__ (KeyError when there is no device implementation --
+    nothing evaluates device data on the host); called with host data they are NumPy."""
+    import numpy as _np
+    if name.startswith("__"):
+        raise AttributeError(name)
+    try:
+        return getattr(_np, name)
+    except AttributeError:
+        raise AttributeError(f"module 'delayrepay' has no attribute {name!r}") from None
 __version__ = "0.1.0"

@@ -716,9 +716,9 @@ def gen_nd(name, prog, ndim, in_class, out_dts, reduce=None, threads=256, wide_i
             w(f"  const {ctype(a.dtype)} x{i} = *reinterpret_cast<const {ctype(a.dtype)}*>(in{i});")
     if reduce is not None:
         w(f"  {A} acc[1]; acc[0] = {_identity(rop, acc_dt)};")
-    w(f"  const {I} total = ({I})g.total;")
+    w(f"  const {I} n_total = ({I})g.total;")
     w(f"  const {I} step = ({I})gridDim.x * blockDim.x;")
-    w(f"  for ({I} idx = ({I})blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += step) {{")
+    w(f"  for ({I} idx = ({I})blockIdx.x * blockDim.x + threadIdx.x; idx < n_total; idx += step) {{")
     w(f"    {I} rem = idx;")
     w(f"    i64 off[{max(n_ops, 1)}];")
     w(f"#pragma unroll\n    for (int k = 0; k < {max(n_ops, 1)}; ++k) off[k] = 0;")
@@ -782,9 +782,9 @@ def _gen_nd_vec(name, prog, ndim, in_class, out_dts, V, threads, wide_index, scl
     for i, (a, c) in enumerate(zip(arrays, in_class)):
         if c == "b":
             w(f"  const {ctype(a.dtype)} x{i} = *reinterpret_cast<const {ctype(a.dtype)}*>(in{i});")
-    w(f"  const {I} total = ({I})g.total;")
+    w(f"  const {I} n_total = ({I})g.total;")
     w(f"  const {I} step = ({I})gridDim.x * blockDim.x;")
-    w(f"  for ({I} idx = ({I})blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += step) {{")
+    w(f"  for ({I} idx = ({I})blockIdx.x * blockDim.x + threadIdx.x; idx < n_total; idx += step) {{")
     w(f"    {I} rem = idx;")
     w(f"    i64 off[{max(n_ops, 1)}];")
     w(f"#pragma unroll\n    for (int k = 0; k < {max(n_ops, 1)}; ++k) off[k] = 0;")

@@ -166,16 +166,21 @@ class DelayArray(numpy.lib.mixins.NDArrayOperatorsMixin):
     def __len__(self):
         return self.shape[0]
 
-    def item(self):
-        return self.get().item()
+    def item(self, *args):
+        return self.get().item(*args)
+
+    def __index__(self):
+        return self.get().__index__()
 
     # ---- capture  [delayarray.py:46-61]
     def __array_ufunc__(self, ufunc, method, *inputs, **kwargs):
         out = kwargs.pop("out", None)
-        if out is not None or kwargs.pop("where", True) is not True:
+        if kwargs.pop("where", True) is not True:
             return NotImplemented
         dtype = kwargs.pop("dtype", None)
         name = ufunc.__name__
+        if out is not None and (method != "__call__" or ufunc.nout != 1 or name == "matmul"):
+            return NotImplemented
         if method == "reduce":
             if name not in _REDUCE_UFUNCS:
                 raise KeyError(name)
@@ -187,8 +192,12 @@ class DelayArray(numpy.lib.mixins.NDArrayOperatorsMixin):
         if name == "matmul":
             return self._dot(inputs, kwargs)
         args = [arg_to_numpy_ex(arg) for arg in inputs]
+        if name == "divmod":
+            return create_ex(np.floor_divide, args), create_ex(np.remainder, args)
         res = create_ex(ufunc, args)
-        return res if dtype is None else res.astype(dtype)
+        if dtype is not None:
+            res = res.astype(dtype)
+        return res if out is None else _store_out(res, out)
 
     def __array_function__(self, func, types, args, kwargs):        # [delayarray.py:87-90]
         if func.__name__ == "dot":
@@ -252,7 +261,14 @@ class DelayArray(numpy.lib.mixins.NDArrayOperatorsMixin):
 
     def __setitem__(self, key, item):
         if isinstance(key, DelayArray):
-            raise NotImplementedError("boolean / integer-array assignment is not supported yet")
+            # a[mask] = scalar (or an array of a's shape): one fused select written in place
+            val = arg_to_numpy_ex(item)
+            if key.dtype != np.dtype(bool) or tuple(key.shape) != tuple(self.shape) \
+                    or tuple(val.shape) not in ((), tuple(self.shape)):
+                raise NotImplementedError("only a[mask] = value with a boolean mask of a's shape "
+                                          "and a scalar or same-shape value is supported")
+            self._force()[...] = WhereEx(key, val, self)
+            return
         self._force()[key] = item
 
     # ---- conveniences of the reference object  [delayarray.py:130-146]
@@ -291,6 +307,72 @@ class DelayArray(numpy.lib.mixins.NDArrayOperatorsMixin):
 
     def copy(self):
         return NPArray(self._force().copy())
+
+    def ravel(self):
+        return self.reshape(-1)
+
+    def flatten(self):
+        return NPArray(self._force().copy().reshape(-1))
+
+    def squeeze(self, axis=None):
+        return np.squeeze(self, axis)
+
+    def swapaxes(self, a, b):
+        return np.swapaxes(self, a, b)
+
+    def any(self, *args, **kwargs):
+        return np.any(self, *args, **kwargs)
+
+    def all(self, *args, **kwargs):
+        return np.all(self, *args, **kwargs)
+
+    def argmax(self, *args, **kwargs):
+        return np.argmax(self, *args, **kwargs)
+
+    def argmin(self, *args, **kwargs):
+        return np.argmin(self, *args, **kwargs)
+
+    def round(self, decimals=0):
+        return np.round(self, decimals)
+
+    def clip(self, a_min=None, a_max=None):
+        return np.clip(self, a_min, a_max)
+
+    def cumsum(self, *args, **kwargs):
+        return np.cumsum(self, *args, **kwargs)
+
+    def fill(self, value):
+        self._force().fill(value)
+
+    def conj(self):
+        return self
+
+    conjugate = conj
+
+    def tolist(self):
+        return self.get().tolist()
+
+    def __iter__(self):
+        if not self.shape:
+            raise TypeError("iteration over a 0-d array")
+        for i in range(self.shape[0]):
+            yield self[i]
+
+    @property
+    def real(self):
+        return self
+
+    @property
+    def imag(self):
+        return zeros_like(self)
+
+    @property
+    def itemsize(self):
+        return self.dtype.itemsize
+
+    @property
+    def nbytes(self):
+        return self.size * self.dtype.itemsize
 
     @property
     def T(self):
@@ -393,7 +475,7 @@ def resolve_loop(ufunc, kids):
             res = ufunc.resolve_dtypes(tuple(np.result_type(s) for s in sig) + (None,) * ufunc.nout)
         hit = (tuple(res[:ufunc.nin]), res[ufunc.nin])
         for dt in hit[0] + (hit[1],):
-            if dt.kind not in "biuf":
+            if dt.kind not in "biuf" or dt.char == "e":
                 raise TypeError(f"{ufunc.__name__}: dtype {dt} is not supported on the device")
         _RESOLVE_CACHE[key] = hit
     return hit
@@ -535,7 +617,8 @@ class WhereEx(NumpyEx):
         super().__init__()
         self.func = np.where
         self.children = [cond, a, b]
-        sig = [k.weak_type if (isinstance(k, Scalar) and k.weak_type is not None) else k.dtype
+        # Python scalars are weak (NEP 50): pass the VALUE, the type `float` would mean float64
+        sig = [k.val if (isinstance(k, Scalar) and k.weak_type is not None) else k.dtype
                for k in (a, b)]
         out = np.result_type(*sig)
         self.loop, self.dtype = (np.dtype(bool), out, out), out
@@ -1087,7 +1170,308 @@ def cumsum(arr, axis=None, dtype=None, out=None):                # [delayarray.p
     return NPArray(engine.cumsum(node._force(), axis))
 
 
+def _store_out(res, out):
+    """ufunc(..., out=target) and the in-place operators (`a += b` arrives here through
+    NDArrayOperatorsMixin).  A leaf is written in place -- its views see the new values, as in
+    NumPy; a lazy expression has no storage of its own, so the result simply replaces it
+    (what the reference does for every target: it ignores `out`, delayarray.py:46)."""
+    target = out[0] if isinstance(out, tuple) else out
+    if isinstance(target, DelayArray):
+        if not np.can_cast(res.dtype, target.dtype, "same_kind"):
+            raise TypeError(f"Cannot cast ufunc output from {res.dtype} to {target.dtype} "
+                            "with casting rule 'same_kind'")
+        if isinstance(target, NPArray) and _backend.is_ndarray(target.array):
+            target.array[...] = res
+            return target
+        if tuple(res.shape) != tuple(target.shape):
+            raise ValueError(f"non-broadcastable output operand with shape {target.shape}")
+        return res.astype(target.dtype)
+    if _backend.is_ndarray(target):
+        target[...] = res
+        return target
+    if isinstance(target, np.ndarray):
+        target[...] = res.get()
+        return target
+    return NotImplemented
+
+
+@implements(np.any)
+def any(arr, axis=None, out=None, keepdims=False, **kw):          # noqa: A001
+    return _reduce(np.maximum, np.not_equal(arg_to_numpy_ex(arr), 0), axis, None, out, keepdims)
+
+
+@implements(np.all)
+def all(arr, axis=None, out=None, keepdims=False, **kw):          # noqa: A001
+    return _reduce(np.minimum, np.not_equal(arg_to_numpy_ex(arr), 0), axis, None, out, keepdims)
+
+
+@implements(np.count_nonzero)
+def count_nonzero(arr, axis=None, keepdims=False):
+    return _reduce(np.add, np.not_equal(arg_to_numpy_ex(arr), 0), axis, np.intp, None, keepdims)
+
+
+def _arg_extreme(arr, axis, keepdims, red):
+    """argmax / argmin as two fused reductions: the extreme value, then the smallest index that
+    holds it (a nan counts as the extreme, first one wins -- NumPy's rule)."""
+    x = arg_to_numpy_ex(arr)
+    if x.size == 0:
+        raise ValueError("attempt to get argmax of an empty sequence")
+    if axis is None:
+        x = x.reshape(-1)
+        ax = 0
+    else:
+        ax = int(axis) % x.ndim
+    n = x.shape[ax]
+    iota = arange(n, dtype=np.intp).reshape((n,) + (1,) * (x.ndim - 1 - ax))
+    best = red(x, axis=ax, keepdims=True)
+    hit = np.equal(x, best)
+    if x.dtype.kind == "f":
+        hit = np.logical_or(hit, np.isnan(x))
+    idx = np.min(np.where(hit, iota, n), axis=ax, keepdims=True)
+    if axis is None:
+        return idx.reshape(()) if not keepdims else idx.reshape((1,) * arg_to_numpy_ex(arr).ndim)
+    return idx if keepdims else idx.reshape(idx.shape[:ax] + idx.shape[ax + 1:])
+
+
+@implements(np.argmax)
+def argmax(arr, axis=None, out=None, keepdims=False):
+    return _arg_extreme(arr, axis, keepdims, np.max)
+
+
+@implements(np.argmin)
+def argmin(arr, axis=None, out=None, keepdims=False):
+    return _arg_extreme(arr, axis, keepdims, np.min)
+
+
+@implements(np.ptp)
+def ptp(arr, axis=None, out=None, keepdims=False):
+    x = arg_to_numpy_ex(arr)
+    return np.max(x, axis=axis, keepdims=keepdims) - np.min(x, axis=axis, keepdims=keepdims)
+
+
+@implements(np.trace)
+def trace(arr, offset=0, **kw):
+    return np.sum(diag(arr, offset))
+
+
+def _dev(a):
+    """backend array of anything array-like (forces a lazy node)"""
+    return arg_to_numpy_ex(a if not np.isscalar(a) else np.asarray(a))._force()
+
+
+@implements(np.reshape)
+def reshape(arr, *args, **kwargs):
+    shape = kwargs.pop("shape", None) or kwargs.pop("newshape", None) or args[0]
+    return arg_to_numpy_ex(arr).reshape(shape)
+
+
+@implements(np.ravel)
+def ravel(arr, order="C"):
+    return arg_to_numpy_ex(arr).reshape(-1)
+
+
+@implements(np.squeeze)
+def squeeze(arr, axis=None):
+    dev = _dev(arr)
+    if axis is None:
+        keep = [i for i, n in enumerate(dev.shape) if n != 1]
+    else:
+        drop = {a % dev.ndim for a in ((axis,) if isinstance(axis, (int, np.integer)) else axis)}
+        if builtins_any(dev.shape[a] != 1 for a in drop):
+            raise ValueError("cannot select an axis to squeeze out which has size not equal to one")
+        keep = [i for i in range(dev.ndim) if i not in drop]
+    return NPArray(DeviceArray(dev.buf, tuple(dev.shape[i] for i in keep), dev.dtype,
+                               tuple(dev.strides[i] for i in keep), dev.offset))
+
+
+@implements(np.expand_dims)
+def expand_dims(arr, axis):
+    dev = _dev(arr)
+    axes = sorted(a % (dev.ndim + (1 if isinstance(axis, (int, np.integer)) else len(axis)))
+                  for a in ((axis,) if isinstance(axis, (int, np.integer)) else axis))
+    shape, strides = list(dev.shape), list(dev.strides)
+    for a in axes:
+        shape.insert(a, 1)
+        strides.insert(a, 0)
+    return NPArray(DeviceArray(dev.buf, tuple(shape), dev.dtype, tuple(strides), dev.offset))
+
+
+@implements(np.swapaxes)
+def swapaxes(arr, a, b):
+    dev = _dev(arr)
+    order = list(range(dev.ndim))
+    order[a], order[b] = order[b], order[a]
+    return NPArray(dev.transpose(order))
+
+
+@implements(np.moveaxis)
+def moveaxis(arr, source, destination):
+    dev = _dev(arr)
+    src = [s % dev.ndim for s in ((source,) if isinstance(source, (int, np.integer)) else source)]
+    dst = [d % dev.ndim for d in ((destination,) if isinstance(destination, (int, np.integer))
+                                  else destination)]
+    order = [i for i in range(dev.ndim) if i not in src]
+    for d, s_ in sorted(zip(dst, src)):
+        order.insert(d, s_)
+    return NPArray(dev.transpose(order))
+
+
+@implements(np.broadcast_to)
+def broadcast_to(arr, shape, subok=False):
+    return NPArray(_dev(arr).broadcast_to(tuple(shape) if not isinstance(shape, (int, np.integer))
+                                          else (int(shape),)))
+
+
+@implements(np.concatenate)
+def concatenate(arrays, axis=0, out=None, dtype=None, **kw):
+    parts = [arg_to_numpy_ex(a) for a in arrays]
+    if axis is None:
+        parts, axis = [p_.reshape(-1) for p_ in parts], 0
+    nd = parts[0].ndim
+    axis %= nd
+    for p_ in parts:
+        if p_.ndim != nd or builtins_any(p_.shape[i] != parts[0].shape[i] for i in range(nd) if i != axis):
+            raise ValueError("all the input array dimensions except for the concatenation axis "
+                             "must match exactly")
+    dt = np.dtype(dtype) if dtype is not None else np.result_type(*[p_.dtype for p_ in parts])
+    total = _builtins.sum(p_.shape[axis] for p_ in parts)
+    shape = parts[0].shape[:axis] + (total,) + parts[0].shape[axis + 1:]
+    res = DeviceArray.empty(shape, dt, _dev(parts[0]).dev) if out is None else _dev(out)
+    at = 0
+    for p_ in parts:
+        n = p_.shape[axis]
+        if n:
+            res[tuple(slice(at, at + n) if i == axis else slice(None) for i in range(nd))] = p_
+        at += n
+    return NPArray(res) if out is None else out
+
+
+@implements(np.stack)
+def stack(arrays, axis=0, out=None, **kw):
+    parts = [arg_to_numpy_ex(a) for a in arrays]
+    ax = axis % (parts[0].ndim + 1)
+    return concatenate([expand_dims(p_, ax) for p_ in parts], axis=ax, out=out)
+
+
+@implements(np.vstack)
+def vstack(tup, **kw):
+    parts = [arg_to_numpy_ex(a) for a in tup]
+    return concatenate([p_.reshape(1, -1) if p_.ndim < 2 else p_ for p_ in parts], axis=0)
+
+
+@implements(np.hstack)
+def hstack(tup, **kw):
+    parts = [arg_to_numpy_ex(a) for a in tup]
+    return concatenate(parts, axis=0 if parts[0].ndim == 1 else 1)
+
+
+@implements(np.outer)
+def outer(a, b, out=None):
+    return arg_to_numpy_ex(a).reshape(-1, 1) * arg_to_numpy_ex(b).reshape(1, -1)
+
+
+@implements(np.inner)
+def inner(a, b):
+    a, b = arg_to_numpy_ex(a), arg_to_numpy_ex(b)
+    if a.ndim == 1 and b.ndim == 1:
+        return DotEx(a, b)
+    raise NotImplementedError("np.inner is supported for vectors only")
+
+
+@implements(np.vdot)
+def vdot(a, b):
+    return DotEx(arg_to_numpy_ex(a).reshape(-1), arg_to_numpy_ex(b).reshape(-1))
+
+
+@implements(np.diff)
+def diff(arr, n=1, axis=-1, **kw):
+    if kw.get("prepend", np._NoValue) is not np._NoValue or kw.get("append", np._NoValue) is not np._NoValue:
+        raise NotImplementedError("np.diff: prepend / append are not supported")
+    x = arg_to_numpy_ex(arr)
+    axis %= x.ndim
+    hi = tuple(slice(1, None) if i == axis else slice(None) for i in range(x.ndim))
+    lo = tuple(slice(None, -1) if i == axis else slice(None) for i in range(x.ndim))
+    for _ in range(n):
+        x = np.not_equal(x[hi], x[lo]) if x.dtype == np.dtype(bool) else x[hi] - x[lo]
+    return x
+
+
+@implements(np.round)
+def round(arr, decimals=0, out=None):                             # noqa: A001
+    x = arg_to_numpy_ex(arr)
+    if x.dtype.kind != "f":
+        if decimals >= 0:
+            return x
+        raise NotImplementedError("rounding integers to negative decimals is not supported")
+    if decimals == 0:
+        return np.rint(x)
+    # NumPy's own recipe: scale by a power of ten, rint, scale back (same roundings)
+    scale = x.dtype.type(10.0 ** abs(decimals))
+    return np.rint(x * scale) / scale if decimals > 0 else np.rint(x / scale) * scale
+
+
+around = round
+implements(np.around)(round)
+
+
+@implements(np.isclose)
+def isclose(a, b, rtol=1e-05, atol=1e-08, equal_nan=False):
+    x, y = arg_to_numpy_ex(a), arg_to_numpy_ex(b)
+    near = np.less_equal(np.absolute(x - y), atol + rtol * np.absolute(y))
+    res = np.where(np.logical_and(np.isfinite(x), np.isfinite(y)), near, np.equal(x, y))
+    if equal_nan:
+        res = np.logical_or(res, np.logical_and(np.isnan(x), np.isnan(y)))
+    return res
+
+
+@implements(np.allclose)
+def allclose(a, b, rtol=1e-05, atol=1e-08, equal_nan=False):
+    return bool(np.all(isclose(a, b, rtol, atol, equal_nan)).get())
+
+
+@implements(np.array_equal)
+def array_equal(a, b, equal_nan=False):
+    x, y = arg_to_numpy_ex(a), arg_to_numpy_ex(b)
+    if tuple(x.shape) != tuple(y.shape):
+        return False
+    eq = np.equal(x, y)
+    if equal_nan:
+        eq = np.logical_or(eq, np.logical_and(np.isnan(x), np.isnan(y)))
+    return bool(np.all(eq).get())
+
+
+@implements(np.shape)
+def shape(arr):
+    return tuple(arg_to_numpy_ex(arr).shape)
+
+
+@implements(np.size)
+def size(arr, axis=None):
+    x = arg_to_numpy_ex(arr)
+    return x.size if axis is None else x.shape[axis]
+
+
+@implements(np.ndim)
+def ndim(arr):
+    return arg_to_numpy_ex(arr).ndim
+
+
+@implements(np.copy)
+def _copy(arr, **kw):
+    return arg_to_numpy_ex(arr).copy()
+
+
+def _like(filler):
+    def make(arr, *args, dtype=None, shape=None, **kw):
+        x = arg_to_numpy_ex(arr)
+        shp = tuple(x.shape) if shape is None else shape
+        dt = x.dtype if dtype is None else dtype
+        return filler(shp, *args, dtype=dt)
+    return make
+
+
 import builtins as _builtins          # noqa: E402
+builtins_any = _builtins.any
 builtins_max, builtins_min = _builtins.max, _builtins.min
 
 
@@ -1151,6 +1535,11 @@ zeros = cast(_backend.fallback.zeros)
 zeros_like = cast(_backend.fallback.zeros_like)
 full = cast(_backend.fallback.full)
 full_like = cast(_backend.fallback.full_like)
+
+implements(np.zeros_like)(_like(lambda shp, dtype: zeros(shp, dtype=dtype)))
+implements(np.ones_like)(_like(lambda shp, dtype: ones(shp, dtype=dtype)))
+implements(np.empty_like)(_like(lambda shp, dtype: empty(shp, dtype=dtype)))
+implements(np.full_like)(_like(lambda shp, fill_value, dtype: full(shp, fill_value, dtype=dtype)))
 
 array = cast(_backend.fallback.array)                            # [delayarray.py:620-631]
 asarray = cast(_backend.fallback.asarray)

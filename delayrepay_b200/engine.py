@@ -593,7 +593,12 @@ def _run_reduce(node):
     result = DeviceArray.empty(node.shape, res_dt, dev)
     node._stamp = _stamp_of(prog)
     if child.size == 0:
-        result.fill(0)
+        # NumPy's identities: sum 0, prod 1, mean nan (0/0); max/min of nothing is an error
+        if count == 0 and op in ("max", "min"):
+            raise ValueError(f"zero-size array to reduction operation {op}imum which has no identity")
+        if result.size:
+            result.fill(float("nan") if node.post == "mean" and res_dt.kind == "f"
+                        else 1 if op == "prod" else 0)
         return result
     if full or not axes:
         if not axes:        # reduction over nothing: a copy

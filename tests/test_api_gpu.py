@@ -1,0 +1,152 @@
+"""The NumPy surface around the hot path (callers): every case is the
+same NumPy-level program run on host arrays by NumPy (what the reference's CPU backend would
+compute after forcing, delayarray.py:511-568) and on DelayArrays by the engine; results must be
+identical (arithmetic only, so bit-exact), shapes and dtypes included.  The reference raises
+KeyError for most of these functions; here they are device implementations (no host fallback).
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+A = np.random.default_rng(5).standard_normal((6, 8))
+B = np.random.default_rng(6).standard_normal((6, 8))
+V = np.random.default_rng(7).standard_normal(48)
+I = np.random.default_rng(8).integers(-9, 9, (6, 8))
+
+CASES = {
+    "any_all": lambda a, b, v, i: (np.any(a > 2.5), np.all(a > -9.0), np.any(a > 0, axis=0), np.all(i, axis=1),
+                                   (a > 0).any(), (a > 0).all(axis=1)),
+    "count_nonzero": lambda a, b, v, i: (np.count_nonzero(i), np.count_nonzero(i, axis=0)),
+    "argmax_argmin": lambda a, b, v, i: (np.argmax(v), np.argmin(v), np.argmax(a, axis=0), np.argmin(a, axis=1),
+                                         np.argmax(i), np.argmax(a * b), a.argmax(axis=1), np.argmax(i, axis=1)),
+    "ptp_trace": lambda a, b, v, i: (np.ptp(a), np.ptp(a, axis=0), np.trace(a[:, :6]), np.trace(a, 1)),
+    "reshape_family": lambda a, b, v, i: (np.reshape(v, (6, 8)) + a, np.ravel(a) * v, a.ravel(), a.T.flatten(),
+                                          np.squeeze(a[:, None, :]) - b, np.expand_dims(v, 0), np.expand_dims(a, (0, 2)),
+                                          np.swapaxes(a, 0, 1), np.moveaxis(a[None], 0, 2), a.swapaxes(1, 0) * 2.0,
+                                          np.squeeze(a[None], axis=0)),
+    "broadcast_to": lambda a, b, v, i: (np.broadcast_to(a[0], (3, 8)) + 1.0, np.broadcast_to(v[:8], (6, 8)) * a),
+    "concatenate": lambda a, b, v, i: (np.concatenate([a, b]), np.concatenate([a, b * 2, a - b], axis=1),
+                                       np.concatenate([v, v[:5] + 1.0]), np.concatenate([a, i]),
+                                       np.concatenate([a, b], axis=None), np.stack([a, b]), np.stack([v, v * 2], axis=1),
+                                       np.vstack([v, v]), np.hstack([a, b]), np.hstack([v, v])),
+    "outer_inner_vdot": lambda a, b, v, i: (np.outer(v[:5], v[5:9]), np.outer(a, b[0])),
+    "diff": lambda a, b, v, i: (np.diff(v), np.diff(a, axis=0), np.diff(a, n=2), np.diff(i), np.diff(a > 0)),
+    "round": lambda a, b, v, i: (np.round(a), np.round(a * 100, 1), np.around(a, 2), np.round(a * 1000, -2), a.round(3),
+                                 np.round(i)),
+    "isclose": lambda a, b, v, i: (np.isclose(a, a + 1e-9), np.isclose(a, b), np.isclose(a / (i * 1.0), a / (i * 1.0)),
+                                   np.isclose(a / (i * 1.0), a / (i * 1.0), equal_nan=True)),
+    "shape_size_ndim": lambda a, b, v, i: (np.shape(a + b), np.size(a), np.size(a, 1), np.ndim(a * 2), (a + b).nbytes,
+                                           (a + b).itemsize, len(a + b)),
+    "like": lambda a, b, v, i: (np.zeros_like(a), np.ones_like(a + b), np.full_like(i, 7), np.full_like(a, 2.5),
+                                np.zeros_like(a, dtype=np.float32), np.empty_like(a).shape, np.ones_like(i, shape=(3,))),
+    "divmod": lambda a, b, v, i: divmod(a, b) + divmod(i, 4) + (np.divmod(a, 0.75)[1],),
+    "out_kw": lambda a, b, v, i: (np.add(a, b, out=np.zeros_like(a)), np.multiply(a, 2.0, out=np.empty_like(a)),
+                                  np.sqrt(abs(a), out=np.ones_like(a))),
+    "copy_real": lambda a, b, v, i: (np.copy(a), a.real, a.imag, a.conj(), (a + b).copy()),
+    "iteration": lambda a, b, v, i: tuple(row * 2.0 for row in a) + ([float(x) for x in v[:4]],),
+    "tolist_item": lambda a, b, v, i: ((a + b).tolist(), np.sum(i).item(), (a * 2)[1, 2].item(), v[3].item()),
+    "methods": lambda a, b, v, i: (a.clip(-0.5, 0.5), v.cumsum(), (a * b).squeeze(), a.any(), i.all()),
+}
+
+
+RTOL = {"ptp_trace": 1e-12}        # trace is a float64 sum: the reduction bar, not bit-exactness
+
+
+def _same(got, want, where):
+    if isinstance(want, (tuple, list)) and not isinstance(got, np.ndarray):
+        assert len(got) == len(want), where
+        for k, (g, w) in enumerate(zip(got, want)):
+            _same(g, w, f"{where}[{k}]")
+        return
+    if hasattr(got, "get"):
+        got = got.get()
+    if isinstance(want, np.ndarray) or isinstance(want, np.generic):
+        got, want = np.asarray(got), np.asarray(want)
+        assert got.shape == want.shape, f"{where}: shape {got.shape} != {want.shape}"
+        assert got.dtype == want.dtype, f"{where}: dtype {got.dtype} != {want.dtype}"
+        rtol = RTOL.get(where.split("[")[0])
+        if rtol:
+            np.testing.assert_allclose(got, want, rtol=rtol, atol=0, err_msg=where)
+        else:
+            assert np.array_equal(got, want, equal_nan=want.dtype.kind == "f"), f"{where}: values differ"
+    else:
+        assert got == want, f"{where}: {got!r} != {want!r}"
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_numpy_surface_matches_numpy(gpu, name):
+    with np.errstate(all="ignore"):
+        want = CASES[name](A.copy(), B.copy(), V.copy(), I.copy())
+    got = CASES[name](gpu.array(A), gpu.array(B), gpu.array(V), gpu.array(I))
+    _same(got, want, name)
+
+
+def test_inplace_operators_write_through_views(gpu):
+    a = A.copy()
+    d = gpu.array(A)
+    row_h, row_d = a[2], d[2]                    # views taken BEFORE the updates
+    for f in (lambda x, y: x.__iadd__(y), lambda x, y: x.__imul__(y), lambda x, y: x.__isub__(y * 0.5),
+              lambda x, y: x.__itruediv__(y * y + 1.0)):
+        a = f(a, B)
+        d = f(d, gpu.array(B))
+    a **= 2
+    d **= 2
+    assert np.array_equal(d.get(), a) and np.array_equal(row_d.get(), row_h)
+    lazy = d + 1.0                               # a lazy expression has no storage: rebinding
+    lazy += d
+    assert np.array_equal(lazy.get(), (a + 1.0) + a)
+    i_h, i_d = I.copy(), gpu.array(I)
+    i_h += 3
+    i_d += 3
+    assert np.array_equal(i_d.get(), i_h) and i_d.dtype == i_h.dtype
+    with pytest.raises(TypeError):               # same_kind casting, like NumPy
+        i_d += 1.5
+    host_out = np.zeros_like(A)
+    np.add(gpu.array(A), gpu.array(B), out=host_out)
+    assert np.array_equal(host_out, A + B)
+
+
+def test_masked_assignment(gpu):
+    a, d = A.copy(), gpu.array(A)
+    a[a < 0] = 0.0
+    d[d < 0] = 0.0
+    assert np.array_equal(d.get(), a)
+    a[a > 1] = (B * 3.0)[a > 1]
+    d[d > 1] = gpu.array(B) * 3.0                # same-shape value: taken where the mask holds
+    assert np.array_equal(d.get(), a)
+    i_h, i_d = I.copy(), gpu.array(I)
+    i_h[i_h % 2 == 0] = -1
+    i_d[i_d % 2 == 0] = -1
+    assert np.array_equal(i_d.get(), i_h)
+    with pytest.raises(NotImplementedError):
+        d[gpu.array(np.array([1, 2]))] = 0.0
+
+
+def test_scalar_conversions_and_truthiness(gpu):
+    d = gpu.array(V)
+    s = np.sum(d * d)
+    assert float(s) == float(np.sum(V * V)) or abs(float(s) - float(np.sum(V * V))) < 1e-12
+    assert bool(np.max(d) > 0) is True and bool(np.max(d) > 1e9) is False
+    steps = 0
+    x = gpu.array(np.full(8, 100.0))
+    while np.max(x) > 1.0:                       # a convergence loop terminates (truthiness forces)
+        x = x * 0.5
+        steps += 1
+    assert steps == 7
+    assert int(np.sum(gpu.array(I))) == int(I.sum())
+    assert [int(t) for t in gpu.array(np.arange(3))] == [0, 1, 2]
+    assert np.arange(5)[gpu.array(np.array(3))] == 3
+
+
+def test_module_namespace_passes_numpy_names_through(gpu):
+    import delayrepay as dnp
+    x = dnp.array(A)
+    assert np.array_equal(dnp.floor(x).get(), np.floor(A))
+    assert np.array_equal(dnp.concatenate([x, x]).get(), np.concatenate([A, A]))
+    assert dnp.inf == np.inf and dnp.int8 is np.int8 and dnp.e == np.e
+    assert abs(float(dnp.linalg.norm(x)) - np.linalg.norm(A)) < 1e-12
+    with pytest.raises(KeyError):                # no device implementation: loud, never on the host
+        dnp.sort(x)
+    with pytest.raises(AttributeError):
+        dnp.no_such_name

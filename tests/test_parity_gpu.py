@@ -630,3 +630,58 @@ def test_dense_matmul_tcgen05(gpu, shape):
         ex2 = (a.astype(np.float64) * 2.0 + 1.0) @ (b.astype(np.float64) - 0.5)
         sc2 = np.abs(a * 2.0 + 1.0).astype(np.float64) @ np.abs(b - 0.5).astype(np.float64)
         assert np.all(np.abs(got2 - ex2) <= 1e-5 * sc2)
+
+
+# ------------------------------------------------------------------ found by tools/fuzz_diff.py
+def test_full_reduction_over_strided_and_broadcast_operands(gpu):
+    rng = np.random.default_rng(31)
+    a = rng.standard_normal((301, 130))
+    b = rng.standard_normal((130, 301))
+    c = rng.standard_normal(130)
+    A, B, Cc = gpu.array(a), gpu.array(b), gpu.array(c)
+    for got, want in ((np.sum(A[:, ::2]), np.sum(a[:, ::2])),
+                      (np.sum(A * B.T), np.sum(a * b.T)),
+                      (np.sum(A[1:] + Cc), np.sum(a[1:] + c)),
+                      (np.prod(A[::-1][:5, :3] * 0.5 + 1.0), np.prod(a[::-1][:5, :3] * 0.5 + 1.0)),
+                      (np.mean(abs(A[::3, 1:])), np.mean(abs(a[::3, 1:])))):
+        np.testing.assert_allclose(np.asarray(got.get()), want, rtol=1e-12)
+    assert np.max(A[:, ::2]).get() == np.max(a[:, ::2])
+    assert np.min(A.T[1:]).get() == np.min(a.T[1:])
+
+
+def test_floor_ceil_trunc_keep_integer_and_boolean_operands(gpu):
+    i = np.arange(-5, 6, dtype=np.int32)
+    b = i > 0
+    for fn in (np.floor, np.ceil, np.trunc):
+        for host in (i, i.astype(np.int64), b):
+            got = fn(gpu.array(host)).get()
+            want = fn(host)
+            assert got.dtype == want.dtype and np.array_equal(got, want), (fn.__name__, host.dtype)
+    with pytest.raises(TypeError):                      # float16 loops are not supported
+        np.sqrt(gpu.array(b))
+
+
+def test_where_with_python_scalars_is_weakly_typed(gpu):
+    x = np.linspace(-1, 1, 37, dtype=np.float32)
+    y = np.linspace(2, 3, 37, dtype=np.float64)
+    X, Y = gpu.array(x), gpu.array(y)
+    for got, want in ((np.where(X > 0, X, 0.1), np.where(x > 0, x, 0.1)),
+                      (np.where(X > 0, 2, X), np.where(x > 0, 2, x)),
+                      (np.where(X > 0, X, np.float64(0.1)), np.where(x > 0, x, np.float64(0.1))),
+                      (np.where(X > 0, Y, 1), np.where(x > 0, y, 1)),
+                      (np.where(X > 0, X, 0.1) - Y, np.where(x > 0, x, 0.1) - y)):
+        got = got.get()
+        assert got.dtype == want.dtype
+        assert_bits_equal(got, want, "where")
+
+
+def test_reductions_of_empty_arrays_follow_numpy(gpu):
+    e = gpu.array(np.zeros(0))
+    assert np.sum(e).get() == 0.0 and np.prod(e).get() == 1.0
+    assert np.isnan(np.mean(e * 2.0).get())
+    with pytest.raises(ValueError):
+        np.max(e).get()
+    z = gpu.array(np.zeros((0, 5), dtype=np.float32))
+    assert np.array_equal(np.sum(z, axis=0).get(), np.zeros(5, np.float32))
+    assert np.array_equal(np.prod(z, axis=0).get(), np.ones(5, np.float32))
+    assert np.sum(z, axis=1).get().shape == (0,)
