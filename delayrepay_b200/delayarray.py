@@ -255,19 +255,30 @@ class DelayArray(numpy.lib.mixins.NDArrayOperatorsMixin):
         return NPArray(self._force().reshape(*args, **kwargs))
 
     def __getitem__(self, key):
-        if isinstance(key, DelayArray):
-            raise NotImplementedError("boolean / integer-array indexing is not supported yet")
+        ia = _index_array(key)
+        if ia is not None:
+            # one boolean mask (compaction) or one integer array (gather) along the leading axes
+            from . import extras
+            src = self._force()
+            return NPArray(extras.compress(src, ia) if ia.dtype == np.dtype(bool) else extras.take(src, ia))
         return NPArray(self._force()[key])
 
     def __setitem__(self, key, item):
-        if isinstance(key, DelayArray):
-            # a[mask] = scalar (or an array of a's shape): one fused select written in place
-            val = arg_to_numpy_ex(item)
-            if key.dtype != np.dtype(bool) or tuple(key.shape) != tuple(self.shape) \
-                    or tuple(val.shape) not in ((), tuple(self.shape)):
-                raise NotImplementedError("only a[mask] = value with a boolean mask of a's shape "
-                                          "and a scalar or same-shape value is supported")
-            self._force()[...] = WhereEx(key, val, self)
+        ia = _index_array(key)
+        if ia is not None:
+            from . import extras
+            val = arg_to_numpy_ex(item if not isinstance(item, (list, tuple)) else np.asarray(item))
+            if ia.dtype == np.dtype(bool) and tuple(ia.shape) == tuple(self.shape) and val.shape == ():
+                # a[mask] = scalar: one fused select written in place
+                mask = key if isinstance(key, DelayArray) else NPArray(ia)
+                self._force()[...] = WhereEx(mask, val, self)
+            else:
+                vals = _backend.fallback.asarray(np.asarray(val.val, dtype=self.dtype)) \
+                    if isinstance(val, Scalar) else val._force()
+                if ia.dtype == np.dtype(bool):
+                    extras.put_mask(self._force(), ia, vals)      # one value per selected position
+                else:
+                    extras.put(self._force(), ia, vals)
             return
         self._force()[key] = item
 
@@ -1057,8 +1068,10 @@ def norm(x, ord=None, axis=None, keepdims=False):
 
 @implements(np.where)
 def where(cond, a=None, b=None):
+    if a is None and b is None:
+        return nonzero(cond)
     if a is None or b is None:
-        raise NotImplementedError("single-argument np.where is not supported")
+        raise ValueError("either both or neither of x and y should be given")
     return WhereEx(arg_to_numpy_ex(cond), arg_to_numpy_ex(a), arg_to_numpy_ex(b))
 
 
@@ -1168,6 +1181,84 @@ def cumsum(arr, axis=None, dtype=None, out=None):                # [delayarray.p
     if dtype is not None:
         node = node.astype(dtype)
     return NPArray(engine.cumsum(node._force(), axis))
+
+
+def _index_array(key):
+    """The backend array of an advanced index (DelayArray, DeviceArray, ndarray or list of
+    integers / booleans), None for basic keys.  Tuples that mix arrays with slices are not
+    supported."""
+    if isinstance(key, tuple):
+        if len(key) == 1 and not isinstance(key[0], (slice, int, np.integer, type(None), type(Ellipsis))):
+            return _index_array(key[0])
+        if builtins_any(isinstance(k, (DelayArray, DeviceArray, np.ndarray, list)) for k in key):
+            raise NotImplementedError("index tuples that contain arrays are not supported")
+        return None
+    if isinstance(key, DelayArray):
+        return key._force()
+    if isinstance(key, DeviceArray):
+        return key
+    if isinstance(key, (list, np.ndarray)):
+        host = np.asarray(key)
+        if host.dtype.kind not in "biu":
+            raise IndexError("arrays used as indices must be of integer (or boolean) type")
+        if host.ndim == 0:
+            return None
+        return _backend.fallback.asarray(host)
+    return None
+
+
+@implements(np.take)
+def take(arr, indices, axis=None, out=None, mode="raise"):
+    x = arg_to_numpy_ex(arr)
+    if axis is None:
+        x = x.reshape(-1)
+    elif axis % x.ndim != 0:
+        return swapaxes(swapaxes(x, 0, axis)[indices], 0, axis)
+    return x[indices if not np.isscalar(indices) else int(indices)]
+
+
+@implements(np.compress)
+def compress(condition, arr, axis=None, out=None):
+    x = arg_to_numpy_ex(arr)
+    cond = arg_to_numpy_ex(np.asarray(condition) if isinstance(condition, (list, tuple)) else condition)
+    cond = cond if cond.dtype == np.dtype(bool) else np.not_equal(cond, 0)
+    if axis is None:
+        x = x.reshape(-1)
+    elif axis % x.ndim != 0:
+        return swapaxes(compress(cond, swapaxes(x, 0, axis), 0), 0, axis)
+    return x[:cond.shape[0]][cond]
+
+
+@implements(np.extract)
+def extract(condition, arr):
+    return compress(arg_to_numpy_ex(condition).reshape(-1), arr)
+
+
+@implements(np.flatnonzero)
+def flatnonzero(arr):
+    from . import extras
+    x = arg_to_numpy_ex(arr)
+    mask = x if x.dtype == np.dtype(bool) else np.not_equal(x, 0)
+    return NPArray(extras.flatnonzero(mask._force()))
+
+
+@implements(np.nonzero)
+def nonzero(arr):
+    x = arg_to_numpy_ex(arr)
+    flat = flatnonzero(x)
+    if x.ndim <= 1:
+        return (flat,)
+    out, rem = [], flat
+    for n in reversed(x.shape[1:]):                  # unravel: fused integer arithmetic
+        out.append(np.remainder(rem, n))
+        rem = np.floor_divide(rem, n)
+    out.append(rem)
+    return tuple(reversed(out))
+
+
+@implements(np.argwhere)
+def argwhere(arr):
+    return stack(list(nonzero(arr)), axis=1)
 
 
 def _store_out(res, out):

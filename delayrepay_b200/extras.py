@@ -260,3 +260,217 @@ def pack_complex(src, n_out, complex_dtype):
     a.scalar(1 if is_c else 0, np.int32)
     launch(kern, src.dev, max(1, min(148 * 8, -(-rows * n_out // 256))), 256, a)
     return out
+
+
+# ------------------------------------------------------------------------------ gather / compact
+# Integer-array and boolean-mask indexing (reference delayarray.py:123-128 hands the key to CuPy).
+# Elements move as opaque 1/2/4/8-byte words, so one specialisation per item size and index type.
+_INDEX_SRC = r'''
+// out[i, :] = src[idx[i], :]   (rows of `inner` words; negative indices wrap like NumPy's)
+extern "C" __global__ void __launch_bounds__(256) NAME_take(const W* __restrict__ src,
+    const IDX* __restrict__ idx, W* __restrict__ out, i64 n_idx, i64 inner, i64 n_src) {
+  const i64 total = n_idx * inner;
+  for (i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (i64)gridDim.x * blockDim.x) {
+    const i64 i = k / inner, c = k - i * inner;
+    i64 j = (i64)idx[i];
+    if (j < 0) j += n_src;
+    out[k] = src[j * inner + c];
+  }
+}
+// dst[idx[i], :] = vals[i, :]   (val_rows == 1: one row broadcast to every index)
+extern "C" __global__ void __launch_bounds__(256) NAME_put(W* __restrict__ dst,
+    const IDX* __restrict__ idx, const W* __restrict__ vals, i64 n_idx, i64 inner, i64 n_dst, i64 val_rows) {
+  const i64 total = n_idx * inner;
+  for (i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (i64)gridDim.x * blockDim.x) {
+    const i64 i = k / inner, c = k - i * inner;
+    i64 j = (i64)idx[i];
+    if (j < 0) j += n_dst;
+    dst[j * inner + c] = vals[(val_rows == 1 ? 0 : i) * inner + c];
+  }
+}
+// rows whose mask is set, packed in order: pos = inclusive prefix sum of the mask
+// mode 0: out[pos-1, :] = src[i, :]     1: src[i, :] = out[pos-1, :] (masked assignment)
+// mode 2: out[pos-1] = i (flatnonzero; W = long long, inner = 1)
+extern "C" __global__ void __launch_bounds__(256) NAME_compact(W* __restrict__ src,
+    const unsigned char* __restrict__ mask, const i64* __restrict__ pos, W* __restrict__ out,
+    i64 n, i64 inner, int mode) {
+  const i64 total = n * inner;
+  for (i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (i64)gridDim.x * blockDim.x) {
+    const i64 i = k / inner, c = k - i * inner;
+    if (!mask[i]) continue;
+    const i64 o = (pos[i] - 1) * inner + c;
+    if (mode == 0) out[o] = src[k];
+    else if (mode == 1) src[k] = out[o];
+    else out[o] = (W)i;
+  }
+}
+'''
+_WORD = {1: "unsigned char", 2: "unsigned short", 4: "unsigned int", 8: "unsigned long long"}
+
+
+def _index_kernels(itemsize, idx_dt):
+    key = ("index", itemsize, np.dtype(idx_dt).str)
+    if key + ("take",) in engine._kernels:
+        return {suffix: engine._kernels[key + (suffix,)] for suffix in ("take", "put", "compact")}
+    name = engine.kernel_name(key)
+    src = _INDEX_SRC.replace("NAME", name).replace("IDX", ctype(idx_dt))
+    src = src.replace("W*", _WORD[itemsize] + "*").replace("(W)", f"({_WORD[itemsize]})")
+    _, cubin = engine.compile_source(name, src)
+    out = {}
+    for suffix in ("take", "put", "compact"):
+        k = engine._kernels.get(key + (suffix,))
+        if k is None:
+            k = engine._kernels[key + (suffix,)] = engine.Kernel(f"{name}_{suffix}", src, cubin, {})
+        out[suffix] = k
+    return out
+
+
+def _grid(n):
+    return max(1, min(148 * 8, -(-n // 256)))
+
+
+def _word_size(dt):
+    if dt.itemsize not in _WORD:
+        raise NotImplementedError(f"indexing arrays of {dt}")
+    return dt.itemsize
+
+
+def _check_bounds(idx, n):
+    """IndexError for an out-of-range index, like NumPy (two fused reductions, one sync)."""
+    from .delayarray import NPArray
+    if idx.size == 0 or idx.dev < 0:
+        return
+    lo, hi = int(np.min(NPArray(idx)).get()), int(np.max(NPArray(idx)).get())
+    if lo < -n or hi >= n:
+        bad = lo if lo < -n else hi
+        raise IndexError(f"index {bad} is out of bounds for axis 0 with size {n}")
+
+
+def take(src, idx):
+    """src[idx] for an integer DeviceArray idx of any shape (gathers along axis 0)."""
+    if idx.dtype.kind not in "iu":
+        raise IndexError("arrays used as indices must be of integer (or boolean) type")
+    src = src if src.is_contiguous else src.copy()
+    idx = idx if idx.is_contiguous else idx.copy()
+    if src.ndim == 0:
+        raise IndexError("too many indices for array")
+    n_src = src.shape[0]
+    inner = int(np.prod(src.shape[1:], dtype=np.int64))
+    _check_bounds(idx, n_src)
+    out = DeviceArray.empty(tuple(idx.shape) + tuple(src.shape[1:]), src.dtype, src.dev if src.dev >= 0 else None)
+    if out.size == 0:
+        return out
+    ks = _index_kernels(_word_size(src.dtype), idx.dtype)
+    a = Args()
+    a.ptr(src.ptr); a.ptr(idx.ptr); a.ptr(out.ptr); a.i64(idx.size); a.i64(inner); a.i64(n_src)
+    launch(ks["take"], src.dev, _grid(out.size), 256, a)
+    return out
+
+
+def put(dst, idx, vals):
+    """dst[idx] = vals (integer index array along axis 0; duplicate indices: one of the writes
+    wins, unspecified which -- NumPy keeps the last).  dst must be contiguous."""
+    if idx.dtype.kind not in "iu":
+        raise IndexError("arrays used as indices must be of integer (or boolean) type")
+    if not dst.is_contiguous:
+        raise NotImplementedError("integer-array assignment into a non-contiguous view")
+    idx = idx if idx.is_contiguous else idx.copy()
+    n_dst = dst.shape[0]
+    inner = int(np.prod(dst.shape[1:], dtype=np.int64))
+    _check_bounds(idx, n_dst)
+    row_shape = tuple(dst.shape[1:])
+    full = tuple(idx.shape) + row_shape
+    vals = vals.astype(dst.dtype) if vals.dtype != dst.dtype else vals
+    if tuple(vals.shape) == full:
+        rows = idx.size
+    else:
+        np.broadcast_shapes(tuple(vals.shape), full)                  # raises like NumPy
+        if vals.ndim <= len(row_shape) and vals.size in (1, max(inner, 1)):
+            vals, rows = vals.broadcast_to(row_shape).copy() if tuple(vals.shape) != row_shape else vals, 1
+        else:
+            vals, rows = vals.broadcast_to(full).copy(), idx.size
+    vals = vals if vals.is_contiguous else vals.copy()
+    if idx.size == 0 or dst.size == 0:
+        return
+    ks = _index_kernels(_word_size(dst.dtype), idx.dtype)
+    a = Args()
+    a.ptr(dst.ptr); a.ptr(idx.ptr); a.ptr(vals.ptr); a.i64(idx.size); a.i64(inner); a.i64(n_dst); a.i64(rows)
+    launch(ks["put"], dst.dev, _grid(idx.size * max(inner, 1)), 256, a)
+    dst.buf.version += 1
+
+
+def _mask_layout(src, mask):
+    """(rows, inner) such that mask selects rows of `inner` words of the contiguous src."""
+    if mask.dtype != np.dtype(bool):
+        raise IndexError("boolean index expected")
+    if tuple(mask.shape) != tuple(src.shape[:mask.ndim]):
+        raise IndexError(f"boolean index did not match indexed array: mask shape {tuple(mask.shape)}, "
+                         f"array shape {tuple(src.shape)}")
+    rows = int(np.prod(mask.shape, dtype=np.int64))
+    inner = int(np.prod(src.shape[mask.ndim:], dtype=np.int64))
+    return rows, inner
+
+
+def _mask_positions(mask):
+    mask = mask if mask.is_contiguous else mask.copy()
+    pos = cumsum(mask.reshape(-1), None)                              # intp inclusive prefix
+    if pos.dtype != np.dtype(np.int64):
+        pos = pos.astype(np.int64)
+    count = int(pos[-1:].get()[0]) if (mask.size and mask.dev >= 0) else 0
+    return mask, pos, count
+
+
+def compress(src, mask):
+    """src[mask] for a boolean DeviceArray covering the leading dimensions of src."""
+    src = src if src.is_contiguous else src.copy()
+    rows, inner = _mask_layout(src, mask)
+    mask, pos, count = _mask_positions(mask)
+    out = DeviceArray.empty((count,) + tuple(src.shape[mask.ndim:]), src.dtype, src.dev if src.dev >= 0 else None)
+    if out.size == 0 and src.dev >= 0:
+        return out
+    ks = _index_kernels(_word_size(src.dtype), np.int64)
+    a = Args()
+    a.ptr(src.ptr); a.ptr(mask.ptr); a.ptr(pos.ptr); a.ptr(out.ptr); a.i64(rows); a.i64(inner)
+    a.scalar(0, np.int32)
+    launch(ks["compact"], src.dev, _grid(rows * max(inner, 1)), 256, a)
+    return out
+
+
+def put_mask(dst, mask, vals):
+    """dst[mask] = vals where vals holds one row per selected position (NumPy's compacted form)."""
+    if not dst.is_contiguous:
+        raise NotImplementedError("masked assignment of an array into a non-contiguous view")
+    rows, inner = _mask_layout(dst, mask)
+    mask, pos, count = _mask_positions(mask)
+    want = (count,) + tuple(dst.shape[mask.ndim:])
+    vals = vals.astype(dst.dtype) if vals.dtype != dst.dtype else vals
+    if tuple(vals.shape) != want:
+        if dst.dev >= 0:
+            np.broadcast_shapes(tuple(vals.shape), want)
+            if vals.ndim > len(want) or (vals.ndim == len(want) and vals.shape[0] != count):
+                raise ValueError(f"NumPy boolean array indexing assignment cannot assign {vals.shape[0]} "
+                                 f"input values to the {count} output values where the mask is true")
+            vals = vals.broadcast_to(want).copy()
+    vals = vals if vals.is_contiguous else vals.copy()
+    if count == 0 and dst.dev >= 0:
+        return
+    ks = _index_kernels(_word_size(dst.dtype), np.int64)
+    a = Args()
+    a.ptr(dst.ptr); a.ptr(mask.ptr); a.ptr(pos.ptr); a.ptr(vals.ptr); a.i64(rows); a.i64(inner)
+    a.scalar(1, np.int32)
+    launch(ks["compact"], dst.dev, _grid(rows * max(inner, 1)), 256, a)
+    dst.buf.version += 1
+
+
+def flatnonzero(mask):
+    """Indices (int64) of the set elements of a boolean DeviceArray, flattened, ascending."""
+    mask, pos, count = _mask_positions(mask)
+    out = DeviceArray.empty((count,), np.int64, mask.dev if mask.dev >= 0 else None)
+    if count == 0 and mask.dev >= 0:
+        return out
+    ks = _index_kernels(8, np.int64)
+    a = Args()
+    a.ptr(out.ptr); a.ptr(mask.ptr); a.ptr(pos.ptr); a.ptr(out.ptr); a.i64(mask.size); a.i64(1)
+    a.scalar(2, np.int32)
+    launch(ks["compact"], mask.dev, _grid(mask.size), 256, a)
+    return out

@@ -113,14 +113,17 @@ def test_masked_assignment(gpu):
     d[d < 0] = 0.0
     assert np.array_equal(d.get(), a)
     a[a > 1] = (B * 3.0)[a > 1]
-    d[d > 1] = gpu.array(B) * 3.0                # same-shape value: taken where the mask holds
+    d[d > 1] = (gpu.array(B) * 3.0)[d > 1]       # one value per selected position
+    with pytest.raises(ValueError):
+        d[d > 1] = gpu.array(B) * 3.0            # NumPy: cannot assign 48 values to the selected ones
     assert np.array_equal(d.get(), a)
     i_h, i_d = I.copy(), gpu.array(I)
     i_h[i_h % 2 == 0] = -1
     i_d[i_d % 2 == 0] = -1
     assert np.array_equal(i_d.get(), i_h)
-    with pytest.raises(NotImplementedError):
-        d[gpu.array(np.array([1, 2]))] = 0.0
+    d[gpu.array(np.array([1, 2]))] = 0.0         # integer-array assignment (rows 1 and 2)
+    a[np.array([1, 2])] = 0.0
+    assert np.array_equal(d.get(), a)
 
 
 def test_scalar_conversions_and_truthiness(gpu):
@@ -150,3 +153,59 @@ def test_module_namespace_passes_numpy_names_through(gpu):
         dnp.sort(x)
     with pytest.raises(AttributeError):
         dnp.no_such_name
+
+
+def test_integer_array_and_boolean_mask_indexing(gpu):
+    """a[idx], a[mask], a[idx] = v, a[mask] = values, np.take/compress/extract/nonzero/argwhere:
+    gather, scan-based compaction and scatter kernels (extras.py) -- data movement, so exact."""
+    rng = np.random.default_rng(12)
+    for dt in (np.float64, np.float32, np.int32, np.int64, np.uint8, np.bool_):
+        h = (rng.standard_normal((50, 7)) * 40).astype(dt)
+        v = (rng.standard_normal(100003) * 40).astype(dt)
+        d, dv = gpu.array(h), gpu.array(v)
+        idx = rng.integers(-50, 50, 33)
+        big = rng.integers(-100003, 100003, (4, 1000))
+        cases = [(d[gpu.array(idx)], h[idx]), (d[idx], h[idx]), (d[list(idx[:5])], h[list(idx[:5])]),
+                 (dv[gpu.array(big)], v[big]), (dv[dv > 3], v[v > 3]), (d[d > 3], h[h > 3]),
+                 (d[gpu.array(h[:, 0] > 0)], h[h[:, 0] > 0]), (d[h[:, 1] > 0], h[h[:, 1] > 0]),
+                 (dv[dv > 1e9] if dt != np.bool_ else dv[~dv & dv], v[v > 1e9] if dt != np.bool_ else v[~v & v]),
+                 (np.take(d, [0, 2, -1], axis=1), np.take(h, [0, 2, -1], axis=1)),
+                 (np.take(d, idx[:4]), np.take(h, idx[:4])), (np.take(dv, 7), np.take(v, 7)),
+                 (np.compress(h[0] > 0, d, axis=1), np.compress(h[0] > 0, h, axis=1)),
+                 (np.compress([True, False, True], d, axis=0), np.compress([True, False, True], h, axis=0)),
+                 (np.extract(d > 0, d), np.extract(h > 0, h)), (np.flatnonzero(dv), np.flatnonzero(v)),
+                 (np.argwhere(d > 0), np.argwhere(h > 0)), (d[(gpu.array(idx),)], h[(idx,)])]
+        cases += list(zip(np.nonzero(d > 0), np.nonzero(h > 0))) + list(zip(np.where(dv > 0), np.where(v > 0)))
+        for k, (got, want) in enumerate(cases):
+            got = got.get()
+            assert got.shape == want.shape and got.dtype == want.dtype, (dt, k, got.shape, want.shape, got.dtype)
+            assert np.array_equal(got, want, equal_nan=dt in (np.float32, np.float64)), (dt, k)
+        # assignment (distinct indices: NumPy's order for duplicates is "last wins", ours unspecified)
+        uniq = rng.permutation(50)[:20]
+        h2, d2 = h.copy(), gpu.array(h)
+        h2[uniq] = 1
+        d2[gpu.array(uniq)] = 1
+        assert np.array_equal(d2.get(), h2)
+        rows = (rng.standard_normal((20, 7)) * 9).astype(dt)
+        h2[uniq] = rows
+        d2[uniq] = gpu.array(rows)
+        assert np.array_equal(d2.get(), h2)
+        h2[uniq[:3]] = rows[0]
+        d2[list(uniq[:3])] = rows[0]
+        assert np.array_equal(d2.get(), h2)
+        m = h2 > 0
+        h2[m] = (h2 * 2)[m]
+        d2[d2 > 0] = (d2 * 2)[d2 > 0]
+        assert np.array_equal(d2.get(), h2)
+        rm = h2[:, 0] > 0
+        fill = (rng.standard_normal((int(rm.sum()), 7)) * 5).astype(dt)
+        h2[rm] = fill
+        d2[gpu.array(rm)] = fill
+        assert np.array_equal(d2.get(), h2)
+    with pytest.raises(IndexError):
+        gpu.array(np.arange(5.0))[gpu.array(np.array([1, 5]))]
+    with pytest.raises(IndexError):
+        gpu.array(np.arange(5.0))[np.array([0.5])]
+    with pytest.raises(IndexError):
+        gpu.array(np.arange(6.0))[gpu.array(np.array([True, False]))]
+    assert gpu.array(np.arange(5.0))[gpu.array(np.zeros(0, dtype=np.int64))].get().shape == (0,)
