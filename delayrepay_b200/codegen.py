@@ -833,10 +833,26 @@ def _gen_nd_vec(name, prog, ndim, in_class, out_dts, V, threads, wide_index, scl
 
 
 # --------------------------------------------------------------------------- rows family
-def gen_rows(name, prog, in_class, reduce, mode, threads=256):
+def _emit_lane_operands(w, arrays, in_class, V, indent):
+    """inside the per-lane loop `e`: bind x<i> for every non-broadcast operand"""
+    for i, (a, c) in enumerate(zip(arrays, in_class)):
+        if c == "v":
+            w(f"{indent}const {ctype(a.dtype)} x{i} = vx{i}.v[e];")
+        elif c == "s":
+            w(f"{indent}const {ctype(a.dtype)} x{i} = sx{i}[e];")
+        elif c == "i":
+            w(f"{indent}const {ctype(a.dtype)} x{i} = ix{i};")
+
+
+def gen_rows(name, prog, in_class, reduce, mode, threads=256, V=1):
     """Reduce the trailing axis of a (rows, cols) space.  Geometry per operand: byte stride
     along rows and along cols (either may be 0 = broadcast).  mode 'warp': one warp per row
-    (short rows), 'block': one block per row (long rows)."""
+    (short rows), 'block': one block per row (long rows).
+
+    in_class per operand: 'b' one value for the whole space, 'v' contiguous along cols and
+    16-byte aligned rows (one 128-bit load per V elements), 'i' constant along cols (one scalar
+    load per row pass), 's' any other stride (scalar loads).  V > 1 requires cols % V == 0.
+    Every thread keeps V independent accumulators and two trips in flight."""
     arrays, scalars = prog.arrays, prog.scalars
     rop, acc_dt, res_dt, post = reduce
     A = ctype(acc_dt)
@@ -851,6 +867,7 @@ def gen_rows(name, prog, in_class, reduce, mode, threads=256):
         params.append(f"const {ctype(dt)} s{j}")
     params += ["char* __restrict__ result", "const double post_scale"]
     body = emit_body(prog)
+    ident = _identity(rop, acc_dt)
     w(f'extern "C" __global__ void __launch_bounds__({threads}) {name}({", ".join(params)}) {{')
     for i, (a, c) in enumerate(zip(arrays, in_class)):
         if c == "b":
@@ -867,22 +884,35 @@ def gen_rows(name, prog, in_class, reduce, mode, threads=256):
         w("  const int lane = threadIdx.x;")
         w(f"  __shared__ {A} scratch[32];")
     w("  for (i64 r = row0; r < g.rows; r += row_step) {")
-    w(f"    {A} acc = {_identity(rop, acc_dt)};")
-    w("    for (i64 c = lane; c < g.cols; c += lanes) {")
+    w(f"    {A} acc[{V}];")
+    w(f"#pragma unroll\n    for (int e = 0; e < {V}; ++e) acc[e] = {ident};")
     for i, (a, c) in enumerate(zip(arrays, in_class)):
-        if c != "b":
-            w(f"      const {ctype(a.dtype)} x{i} = *reinterpret_cast<const {ctype(a.dtype)}*>"
-              f"(in{i} + r * g.rs[{i}] + c * g.cs[{i}]);")
+        if c == "i":
+            w(f"    const {ctype(a.dtype)} ix{i} = *reinterpret_cast<const {ctype(a.dtype)}*>(in{i} + r * g.rs[{i}]);")
+    w(f"#pragma unroll 2\n    for (i64 c = (i64)lane * {V}; c < g.cols; c += (i64)lanes * {V}) {{")
+    for i, (a, c) in enumerate(zip(arrays, in_class)):
+        T = ctype(a.dtype)
+        if c == "v":
+            w(f"      const Vec<{T}, {V}> vx{i} = dr_ld<false, {T}, {V}>(reinterpret_cast<const {T}*>"
+              f"(in{i} + r * g.rs[{i}]) + c);")
+        elif c == "s":
+            w(f"      {T} sx{i}[{V}];")
+            w(f"#pragma unroll\n      for (int e = 0; e < {V}; ++e) sx{i}[e] = *reinterpret_cast<const {T}*>"
+              f"(in{i} + r * g.rs[{i}] + (c + e) * g.cs[{i}]);")
+    w(f"#pragma unroll\n      for (int e = 0; e < {V}; ++e) {{")
+    _emit_lane_operands(w, arrays, in_class, V, "        ")
     for line in body:
-        w(f"      {line}")
-    w(f"      acc = {_RED[rop]}::op(acc, ({A}){_operand_name(prog.roots[0])});")
+        w(f"        {line}")
+    w(f"        acc[e] = {_RED[rop]}::op(acc[e], ({A}){_operand_name(prog.roots[0])});")
+    w("      }")
     w("    }")
+    w(f"#pragma unroll\n    for (int e = 1; e < {V}; ++e) acc[0] = {_RED[rop]}::op(acc[0], acc[e]);")
     if mode == "warp":
-        w(f"    acc = dr_warp_reduce<{_RED[rop]}>(acc);")
+        w(f"    const {A} tot = dr_warp_reduce<{_RED[rop]}>(acc[0]);")
     else:
-        w(f"    acc = dr_block_reduce<{_RED[rop]}>(acc, {_identity(rop, acc_dt)}, scratch);")
-    fin = f"({ctype(res_dt)})(acc / ({A})post_scale)" if np.dtype(acc_dt).kind == "f" \
-        else f"({ctype(res_dt)})acc"
+        w(f"    const {A} tot = dr_block_reduce<{_RED[rop]}>(acc[0], {ident}, scratch);")
+    fin = f"({ctype(res_dt)})(tot / ({A})post_scale)" if np.dtype(acc_dt).kind == "f" \
+        else f"({ctype(res_dt)})tot"
     w(f"    if (lane == 0) *reinterpret_cast<{ctype(res_dt)}*>(result + r * g.out_stride) = {fin};")
     w("  }")
     w("}")
@@ -890,43 +920,68 @@ def gen_rows(name, prog, in_class, reduce, mode, threads=256):
 
 
 # --------------------------------------------------------------------------- cols family
-def gen_cols(name, prog, in_class, reduce, threads=256):
-    """Reduce the MIDDLE axis of an (outer, red, inner) space with inner > 1: one thread per
-    (outer, inner) output element, coalesced along inner, serial over red."""
+def gen_cols(name, prog, in_class, reduce, threads=256, V=1, partial=False):
+    """Reduce the MIDDLE axis of an (outer, red, inner) space with inner > 1: one thread per V
+    consecutive (outer, inner) output elements, coalesced along inner, walking a CHUNK of the
+    reduced axis (blockIdx.y selects the chunk) with four trips in flight.
+
+    partial=False: one chunk covers the axis, results are finished (post scale, cast) and stored.
+    partial=True: each chunk stores its accumulators to out[(o * splits + chunk) * inner + c] in
+    the accumulator type; the same kernel family then reduces the (outer, splits, inner) partials
+    -- fixed order, deterministic.  Operand classes as in gen_rows ('v' = contiguous along inner)."""
     arrays, scalars = prog.arrays, prog.scalars
     rop, acc_dt, res_dt, post = reduce
     A = ctype(acc_dt)
+    OUT = A if partial else ctype(res_dt)
     n_ops = max(len(arrays), 1)
     src = []
     w = src.append
-    w(f"struct Geo_{name} {{ i64 outer; i64 red; i64 inner; i64 so[{n_ops}]; i64 sr[{n_ops}]; i64 si[{n_ops}]; }};")
+    w(f"struct Geo_{name} {{ i64 outer; i64 red; i64 inner; i64 so[{n_ops}]; i64 sr[{n_ops}]; i64 si[{n_ops}]; i64 chunk; }};")
     params = [f"const Geo_{name} g"]
     for i, a in enumerate(arrays):
         params.append(f"const char* __restrict__ in{i}")
     for j, (_, dt) in enumerate(scalars):
         params.append(f"const {ctype(dt)} s{j}")
-    params += [f"{ctype(res_dt)}* __restrict__ result", "const double post_scale"]
+    params += [f"{OUT}* __restrict__ result", "const double post_scale"]
     body = emit_body(prog)
+    ident = _identity(rop, acc_dt)
     w(f'extern "C" __global__ void __launch_bounds__({threads}) {name}({", ".join(params)}) {{')
     for i, (a, c) in enumerate(zip(arrays, in_class)):
         if c == "b":
             w(f"  const {ctype(a.dtype)} x{i} = *reinterpret_cast<const {ctype(a.dtype)}*>(in{i});")
-    w("  const i64 total = g.outer * g.inner;")
+    w(f"  const i64 nvec = g.inner / {V};")
+    w("  const i64 total = g.outer * nvec;")
+    w("  const i64 r0 = (i64)blockIdx.y * g.chunk, r1 = r0 + g.chunk < g.red ? r0 + g.chunk : g.red;")
     w("  for (i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (i64)gridDim.x * blockDim.x) {")
-    w("    const i64 o = idx / g.inner, c = idx - o * g.inner;")
-    w(f"    {A} acc = {_identity(rop, acc_dt)};")
-    w("    for (i64 r = 0; r < g.red; ++r) {")
+    w(f"    const i64 o = idx / nvec, c = (idx - o * nvec) * {V};")
+    w(f"    {A} acc[{V}];")
+    w(f"#pragma unroll\n    for (int e = 0; e < {V}; ++e) acc[e] = {ident};")
+    w("#pragma unroll 4\n    for (i64 r = r0; r < r1; ++r) {")
     for i, (a, c) in enumerate(zip(arrays, in_class)):
-        if c != "b":
-            w(f"      const {ctype(a.dtype)} x{i} = *reinterpret_cast<const {ctype(a.dtype)}*>"
-              f"(in{i} + o * g.so[{i}] + r * g.sr[{i}] + c * g.si[{i}]);")
+        T = ctype(a.dtype)
+        if c == "v":
+            w(f"      const Vec<{T}, {V}> vx{i} = dr_ld<false, {T}, {V}>(reinterpret_cast<const {T}*>"
+              f"(in{i} + o * g.so[{i}] + r * g.sr[{i}]) + c);")
+        elif c == "i":
+            w(f"      const {T} ix{i} = *reinterpret_cast<const {T}*>(in{i} + o * g.so[{i}] + r * g.sr[{i}]);")
+        elif c == "s":
+            w(f"      {T} sx{i}[{V}];")
+            w(f"#pragma unroll\n      for (int e = 0; e < {V}; ++e) sx{i}[e] = *reinterpret_cast<const {T}*>"
+              f"(in{i} + o * g.so[{i}] + r * g.sr[{i}] + (c + e) * g.si[{i}]);")
+    w(f"#pragma unroll\n      for (int e = 0; e < {V}; ++e) {{")
+    _emit_lane_operands(w, arrays, in_class, V, "        ")
     for line in body:
-        w(f"      {line}")
-    w(f"      acc = {_RED[rop]}::op(acc, ({A}){_operand_name(prog.roots[0])});")
+        w(f"        {line}")
+    w(f"        acc[e] = {_RED[rop]}::op(acc[e], ({A}){_operand_name(prog.roots[0])});")
+    w("      }")
     w("    }")
-    fin = f"({ctype(res_dt)})(acc / ({A})post_scale)" if np.dtype(acc_dt).kind == "f" \
-        else f"({ctype(res_dt)})acc"
-    w(f"    result[idx] = {fin};")
+    if partial:
+        w(f"#pragma unroll\n    for (int e = 0; e < {V}; ++e)")
+        w("      result[(o * gridDim.y + blockIdx.y) * g.inner + c + e] = acc[e];")
+    else:
+        fin = f"({ctype(res_dt)})(acc[e] / ({A})post_scale)" if np.dtype(acc_dt).kind == "f" \
+            else f"({ctype(res_dt)})acc[e]"
+        w(f"#pragma unroll\n    for (int e = 0; e < {V}; ++e) result[o * g.inner + c + e] = {fin};")
     w("  }")
     w("}")
     return "\n".join(src) + "\n"

@@ -186,7 +186,7 @@ class DelayArray(numpy.lib.mixins.NDArrayOperatorsMixin):
                 raise KeyError(name)
             res = ReduceEx(ufunc, arg_to_numpy_ex(inputs[0]), _norm_axis(kwargs.get("axis", 0)),
                            bool(kwargs.get("keepdims", False)))
-            return res if dtype is None else res.astype(dtype)
+            return res if dtype is None else as_dtype(res, dtype)
         if method != "__call__":
             return NotImplemented
         if name == "matmul":
@@ -196,7 +196,7 @@ class DelayArray(numpy.lib.mixins.NDArrayOperatorsMixin):
             return create_ex(np.floor_divide, args), create_ex(np.remainder, args)
         res = create_ex(ufunc, args)
         if dtype is not None:
-            res = res.astype(dtype)
+            res = as_dtype(res, dtype)
         return res if out is None else _store_out(res, out)
 
     def __array_function__(self, func, types, args, kwargs):        # [delayarray.py:87-90]
@@ -645,6 +645,14 @@ class WhereEx(NumpyEx):
         return f"where{self._count}"
 
 
+def as_dtype(node, dtype):
+    """A node of the given dtype WITHOUT touching the operand: `leaf.astype` converts the leaf in
+    place (the reference's API, delayarray.py:401-408), which internal code must never do to a
+    user's array."""
+    dtype = np.dtype(dtype)
+    return node if node.dtype == dtype else CastEx(node, dtype)
+
+
 class CastEx(NumpyEx):
     """astype on a lazy node (the reference only has the in-place leaf astype, :401-408)."""
 
@@ -1002,7 +1010,7 @@ def _reduce(ufunc, arr, axis=None, dtype=None, out=None, keepdims=False, post=No
         raise NotImplementedError("out= is not supported")
     node = arg_to_numpy_ex(arr)
     if dtype is not None:
-        node = node.astype(dtype)
+        node = as_dtype(node, dtype)
     if keepdims is np._NoValue:
         keepdims = False
     return ReduceEx(ufunc, node, _norm_axis(axis), bool(keepdims), post)
@@ -1045,7 +1053,7 @@ def average(arr, axis=None, weights=None, **kwargs):            # [delayarray.py
 def var(arr, axis=None, dtype=None, out=None, ddof=0, keepdims=False, **kw):   # [:511-513]
     x = arg_to_numpy_ex(arr)
     if dtype is not None:
-        x = x.astype(dtype)
+        x = as_dtype(x, dtype)
     mu = mean(x, axis=axis, keepdims=True).run()
     dev = x - mu
     ss = np.sum(dev * dev, axis=axis, keepdims=bool(keepdims))
@@ -1179,7 +1187,7 @@ def cumsum(arr, axis=None, dtype=None, out=None):                # [delayarray.p
     from . import engine
     node = arg_to_numpy_ex(arr)
     if dtype is not None:
-        node = node.astype(dtype)
+        node = as_dtype(node, dtype)
     return NPArray(engine.cumsum(node._force(), axis))
 
 
@@ -1276,7 +1284,7 @@ def _store_out(res, out):
             return target
         if tuple(res.shape) != tuple(target.shape):
             raise ValueError(f"non-broadcastable output operand with shape {target.shape}")
-        return res.astype(target.dtype)
+        return as_dtype(res, target.dtype)
     if _backend.is_ndarray(target):
         target[...] = res
         return target
@@ -1301,37 +1309,25 @@ def count_nonzero(arr, axis=None, keepdims=False):
     return _reduce(np.add, np.not_equal(arg_to_numpy_ex(arr), 0), axis, np.intp, None, keepdims)
 
 
-def _arg_extreme(arr, axis, keepdims, red):
-    """argmax / argmin as two fused reductions: the extreme value, then the smallest index that
-    holds it (a nan counts as the extreme, first one wins -- NumPy's rule)."""
+def _arg_extreme(arr, axis, keepdims, is_max):
+    """argmax / argmin: (value, first index) pair reduction on the device (extras.argreduce)."""
+    from . import extras
     x = arg_to_numpy_ex(arr)
-    if x.size == 0:
-        raise ValueError("attempt to get argmax of an empty sequence")
-    if axis is None:
-        x = x.reshape(-1)
-        ax = 0
-    else:
-        ax = int(axis) % x.ndim
-    n = x.shape[ax]
-    iota = arange(n, dtype=np.intp).reshape((n,) + (1,) * (x.ndim - 1 - ax))
-    best = red(x, axis=ax, keepdims=True)
-    hit = np.equal(x, best)
-    if x.dtype.kind == "f":
-        hit = np.logical_or(hit, np.isnan(x))
-    idx = np.min(np.where(hit, iota, n), axis=ax, keepdims=True)
-    if axis is None:
-        return idx.reshape(()) if not keepdims else idx.reshape((1,) * arg_to_numpy_ex(arr).ndim)
-    return idx if keepdims else idx.reshape(idx.shape[:ax] + idx.shape[ax + 1:])
+    res = NPArray(extras.argreduce(x._force(), axis, is_max))
+    if keepdims:
+        res = res.reshape((1,) * x.ndim if axis is None else
+                          x.shape[:axis % x.ndim] + (1,) + x.shape[axis % x.ndim + 1:])
+    return res
 
 
 @implements(np.argmax)
 def argmax(arr, axis=None, out=None, keepdims=False):
-    return _arg_extreme(arr, axis, keepdims, np.max)
+    return _arg_extreme(arr, axis, keepdims, True)
 
 
 @implements(np.argmin)
 def argmin(arr, axis=None, out=None, keepdims=False):
-    return _arg_extreme(arr, axis, keepdims, np.min)
+    return _arg_extreme(arr, axis, keepdims, False)
 
 
 @implements(np.ptp)

@@ -573,7 +573,8 @@ def _run_reduce(node):
     post = float(count) if node.post == "mean" else 1.0
     src = child
     if src.dtype != res_dt:
-        src = child.astype(res_dt)          # e.g. bool/int8 sums accumulate as int64
+        from .delayarray import as_dtype
+        src = as_dtype(child, res_dt)       # e.g. bool/int8 sums accumulate as int64
     acc_dt = codegen.acc_dtype(op, res_dt)
     full = len(axes) == nd
     # non-contiguous axis groups: peel the last contiguous run first
@@ -585,7 +586,8 @@ def _run_reduce(node):
         outer = ReduceEx(node.func, inner, tuple(axes[:run_start]), True)
         res = outer._force()
         if node.post == "mean":
-            res = (NPArray(res) / float(count)).astype(res_dt)._force()
+            from .delayarray import as_dtype
+            res = as_dtype(NPArray(res) / float(count), res_dt)._force()
         return res.reshape(node.shape)
     prog = planner.build_program([src])
     prog.shape = tuple(child.shape)
@@ -638,18 +640,54 @@ def _run_reduce_dense(node, dense, outer, red, inner, op, acc_dt, res_dt, post, 
     return result
 
 
+builtins_all, builtins_any = all, any
+
+
+def _axis_classes(prog, triples, along, other, extent):
+    """Operand classes for the rows / cols kernels and the vector width they allow.
+    along = index in the triple of the axis the threads walk contiguously, other = the indices
+    of the remaining strides (must keep 16-byte alignment for vector loads)."""
+    width = max([a.dtype.itemsize for a in prog.arrays] + [1])
+    V = max(1, 16 // width)
+    cls = []
+    for arr, t in zip(prog.arrays, triples):
+        if t == (0, 0, 0):
+            cls.append("b")
+        elif t[along] == 0:
+            cls.append("i")
+        elif t[along] == arr.dtype.itemsize and arr.dtype.itemsize * V == 16 and arr.ptr % 16 == 0 \
+                and builtins_all(t[k] % 16 == 0 for k in other):
+            cls.append("v")
+        else:
+            cls.append("s")
+    if V > 1 and (extent % V != 0 or "v" not in cls or os.environ.get("DR_NO_AXISVEC")):
+        V = 1
+    if V == 1:
+        cls = ["s" if c == "v" else c for c in cls]
+    return tuple(cls), V
+
+
 def _launch_axis_reduce(prog, triples, outer, red, inner, op, acc_dt, res_dt, post, result, dev):
     st = dev_state(dev)
-    in_class = tuple("b" if t == (0, 0, 0) else "s" for t in triples)
     red_spec = (op, acc_dt, res_dt, None)
     a = Args()
     n_ops = max(len(triples), 1)
     pad = [(0, 0, 0)] * (n_ops - len(triples))
     tr = list(triples) + pad
+    def _bytes_where(axis):          # footprint of the operands that are contiguous along `axis`
+        return sum(arr.dtype.itemsize * (outer if t[0] else 1) * (red if t[1] else 1)
+                   for arr, t in zip(prog.arrays, triples) if t[axis] == arr.dtype.itemsize)
+    if inner == 1 and outer > 1 and triples and _bytes_where(0) > _bytes_where(1):
+        # the operands are contiguous along the KEPT axis (transposed views, `v @ X`): walk it
+        # with the column kernel -- (1, red, outer) with the stride roles swapped -- instead of
+        # reading 4-byte elements a row pitch apart
+        swapped = [(0, t[1], t[0]) for t in triples]
+        return _launch_axis_reduce(prog, swapped, 1, red, outer, op, acc_dt, res_dt, post, result, dev)
     if inner == 1:
+        in_class, V = _axis_classes(prog, triples, 1, (0,), red)
         mode = "block" if red >= 2048 or outer < st.sm_count * 8 else "warp"
-        key = ("rows", prog.key(), in_class, op, acc_dt.str, res_dt.str, mode)
-        kern = get_kernel(key, lambda name: codegen.gen_rows(name, prog, in_class, red_spec, mode))
+        key = ("rows", prog.key(), in_class, op, acc_dt.str, res_dt.str, mode, V)
+        kern = get_kernel(key, lambda name: codegen.gen_rows(name, prog, in_class, red_spec, mode, V=V))
         geo = [outer, red] + [t[0] for t in tr] + [t[1] for t in tr] + [res_dt.itemsize]
         a.raw(np.asarray(geo, dtype=np.int64).tobytes(), 8)
         for arr in prog.arrays:
@@ -661,18 +699,37 @@ def _launch_axis_reduce(prog, triples, outer, red, inner, op, acc_dt, res_dt, po
         cap = st.sm_count * (kern.blocks_per_sm(dev, 256) if dev >= 0 else 8)
         grid = min(outer, cap) if mode == "block" else min(max(1, -(-outer * 32 // 256)), cap)
         launch(kern, dev, grid, 256, a)
-    else:
-        key = ("cols", prog.key(), in_class, op, acc_dt.str, res_dt.str)
-        kern = get_kernel(key, lambda name: codegen.gen_cols(name, prog, in_class, red_spec))
-        geo = [outer, red, inner] + [t[0] for t in tr] + [t[1] for t in tr] + [t[2] for t in tr]
-        a.raw(np.asarray(geo, dtype=np.int64).tobytes(), 8)
-        for arr in prog.arrays:
-            a.ptr(arr.ptr)
-        for val, dt in prog.scalars:
-            a.scalar(val, dt)
-        a.ptr(result.ptr)
-        a.f64(post)
-        launch(kern, dev, _grid_for(kern, dev, 256, outer * inner), 256, a)
+        return
+    in_class, V = _axis_classes(prog, triples, 2, (0, 1), inner)
+    # enough CTAs to fill the machine: split the reduced axis when (outer x inner) alone is small
+    blocks_x = max(1, -(-(outer * (inner // V)) // 256))
+    want = st.sm_count * 8
+    splits = 1
+    if blocks_x < want and red >= 64:
+        splits = min(-(-want // blocks_x), red // 16, 1024)
+    chunk = -(-red // splits)
+    splits = -(-red // chunk)
+    partial = splits > 1
+    key = ("cols", prog.key(), in_class, op, acc_dt.str, res_dt.str, V, partial)
+    kern = get_kernel(key, lambda name: codegen.gen_cols(name, prog, in_class, red_spec, V=V,
+                                                         partial=partial))
+    geo = [outer, red, inner] + [t[0] for t in tr] + [t[1] for t in tr] + [t[2] for t in tr] + [chunk]
+    a.raw(np.asarray(geo, dtype=np.int64).tobytes(), 8)
+    for arr in prog.arrays:
+        a.ptr(arr.ptr)
+    for val, dt in prog.scalars:
+        a.scalar(val, dt)
+    target = DeviceArray.empty((outer, splits, inner), acc_dt, dev if dev >= 0 else None) if partial else result
+    a.ptr(target.ptr)
+    a.f64(post)
+    gx = min(blocks_x, st.sm_count * 16)
+    launch(kern, dev, (gx, splits, 1), 256, a)
+    if partial:
+        from .delayarray import NPArray
+        p2 = planner.build_program([NPArray(target)])
+        item = acc_dt.itemsize
+        _launch_axis_reduce(p2, [(splits * inner * item, inner * item, item)], outer, splits, inner,
+                            op, acc_dt, res_dt, post, result, dev)
 
 
 # --------------------------------------------------------------------------- contractions
@@ -701,8 +758,9 @@ def _run_matmul(node):
     m, k = a.shape
     n = b.shape[1]
     res_dt = node.dtype
-    pa = planner.build_program([a if a.dtype == res_dt else a.astype(res_dt)])
-    pb = planner.build_program([b if b.dtype == res_dt else b.astype(res_dt)])
+    from .delayarray import as_dtype
+    pa = planner.build_program([as_dtype(a, res_dt)])
+    pb = planner.build_program([as_dtype(b, res_dt)])
     prog = planner.Program()
     triples = []
     remap = {}
@@ -727,7 +785,8 @@ def _run_matmul(node):
     skinny = _try_mm_skinny(node, pa, m, k, n, res_dt)
     if skinny is not None:
         return skinny
-    if res_dt == np.float32 and min(m, n) >= 128 and k >= 64 and not os.environ.get("DR_NO_TCGEN05"):
+    if res_dt == np.float32 and min(m, n) >= 8 and max(m, n) >= 128 and k >= 64 \
+            and not os.environ.get("DR_NO_TCGEN05"):
         from . import gemm
         node._stamp = _stamp_of(pa) + _stamp_of(pb)
         return gemm.matmul_tf32x3(a, b)

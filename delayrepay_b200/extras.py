@@ -26,9 +26,79 @@ extern "C" __global__ void __launch_bounds__(256) NAME_serial(const TIN* __restr
     for (i64 k = 0; k < n; ++k) { acc += (TACC)p[k * inner]; q[k * inner] = acc; }
   }
 }
+// rows of a matrix, scanned along the contiguous axis: one block per row walks it in tiles of
+// 256 * ITEMS elements (thread-local scan, warp shuffles, running carry): one read, one write
+#define ITEMS 8
+extern "C" __global__ void __launch_bounds__(256) NAME_rowscan(const TIN* __restrict__ in,
+    TACC* __restrict__ out, i64 rows, i64 n) {
+  __shared__ TACC warp_tot[8];
+  for (i64 r = blockIdx.x; r < rows; r += gridDim.x) {
+    const TIN* p = in + r * n;
+    TACC* q = out + r * n;
+    TACC carry = (TACC)0;
+    for (i64 base = 0; base < n; base += 256 * ITEMS) {
+      const i64 b = base + (i64)threadIdx.x * ITEMS;
+      TACC v[ITEMS], s = (TACC)0;
+#pragma unroll
+      for (int k = 0; k < ITEMS; ++k) { v[k] = b + k < n ? (TACC)p[b + k] : (TACC)0; s += v[k]; v[k] = s; }
+      TACC x = s;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { TACC y = dr_shfl_up(x, o); if ((threadIdx.x & 31) >= o) x += y; }
+      if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = x;
+      __syncthreads();
+      TACC before = carry + (x - s), tile = (TACC)0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) { if (w < (threadIdx.x >> 5)) before += warp_tot[w]; tile += warp_tot[w]; }
+#pragma unroll
+      for (int k = 0; k < ITEMS; ++k) if (b + k < n) q[b + k] = before + v[k];
+      carry += tile;
+      __syncthreads();
+    }
+  }
+}
+// scan along the middle axis with the axis cut into `parts` chunks (enough threads when
+// outer * inner alone is small): (1) chunk totals, (2) exclusive scan of the totals over the
+// chunks, (3) rescan every chunk from its offset.  Coalesced along inner throughout.
+extern "C" __global__ void __launch_bounds__(256) NAME_chunk_totals(const TIN* __restrict__ in,
+    TACC* __restrict__ totals, i64 outer, i64 n, i64 inner, i64 chunk, i64 parts) {
+  const i64 total = outer * parts * inner;
+  for (i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (i64)gridDim.x * blockDim.x) {
+    const i64 c = idx % inner, s = (idx / inner) % parts, o = idx / (inner * parts);
+    const i64 lo = s * chunk, hi = lo + chunk < n ? lo + chunk : n;
+    const TIN* p = in + o * n * inner + c;
+    TACC acc = (TACC)0;
+#pragma unroll 4
+    for (i64 k = lo; k < hi; ++k) acc += (TACC)p[k * inner];
+    totals[idx] = acc;
+  }
+}
+extern "C" __global__ void __launch_bounds__(256) NAME_chunk_offsets(TACC* __restrict__ totals,
+    i64 outer, i64 inner, i64 parts) {
+  const i64 total = outer * inner;
+  for (i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (i64)gridDim.x * blockDim.x) {
+    const i64 o = idx / inner, c = idx - o * inner;
+    TACC acc = (TACC)0;
+    for (i64 s = 0; s < parts; ++s) {
+      TACC* t = totals + (o * parts + s) * inner + c;
+      const TACC v = *t; *t = acc; acc += v;
+    }
+  }
+}
+extern "C" __global__ void __launch_bounds__(256) NAME_chunk_final(const TIN* __restrict__ in,
+    TACC* __restrict__ out, const TACC* __restrict__ totals, i64 outer, i64 n, i64 inner, i64 chunk, i64 parts) {
+  const i64 total = outer * parts * inner;
+  for (i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (i64)gridDim.x * blockDim.x) {
+    const i64 c = idx % inner, s = (idx / inner) % parts, o = idx / (inner * parts);
+    const i64 lo = s * chunk, hi = lo + chunk < n ? lo + chunk : n;
+    const TIN* p = in + o * n * inner + c;
+    TACC* q = out + o * n * inner + c;
+    TACC acc = totals[idx];
+#pragma unroll 4
+    for (i64 k = lo; k < hi; ++k) { acc += (TACC)p[k * inner]; q[k * inner] = acc; }
+  }
+}
 // 1-d, three phases: (1) per-block totals, (2) exclusive scan of the totals by one block,
 // (3) per-block inclusive scan (warp shuffles + shared memory) offset by its prefix
-#define ITEMS 8
 extern "C" __global__ void __launch_bounds__(256) NAME_partials(const TIN* __restrict__ in,
     TACC* __restrict__ totals, i64 n) {
   __shared__ TACC scratch[32];
@@ -105,12 +175,17 @@ def _scan_kernels(in_dt, acc_dt):
     src = _SHFL_UP + _SCAN_SRC.replace("NAME", name).replace("TIN", ctype(in_dt)).replace("TACC", ctype(acc_dt))
     _, cubin = engine.compile_source(name, src)
     out = {}
-    for suffix in ("serial", "partials", "offsets", "final"):
+    for suffix in ("serial", "partials", "offsets", "final", "rowscan", "chunk_totals", "chunk_offsets",
+                   "chunk_final"):
         k = engine._kernels.get(key + (suffix,))
         if k is None:
             k = engine._kernels[key + (suffix,)] = engine.Kernel(f"{name}_{suffix}", src, cubin, {})
         out[suffix] = k
     return out
+
+
+def _grid_1d(n):
+    return max(1, min(148 * 16, -(-n // 256)))
 
 
 def cumsum(arr, axis=None):
@@ -131,6 +206,28 @@ def cumsum(arr, axis=None):
     if src.size == 0:
         return out
     ks = _scan_kernels(in_dt, acc_dt)
+    d = dev if dev >= 0 else None
+    if inner == 1 and outer >= 64 and n >= 64:
+        a = Args()
+        a.ptr(src.ptr); a.ptr(out.ptr); a.i64(outer); a.i64(n)
+        launch(ks["rowscan"], dev, min(outer, 148 * 8), 256, a)
+        return out
+    parts = min(-(-148 * 2048 // max(outer * inner, 1)), n // 16) if inner > 1 else 1
+    if parts > 1:
+        chunk = -(-n // parts)
+        parts = -(-n // chunk)
+        totals = DeviceArray.empty((outer, parts, inner), acc_dt, d)
+        a = Args()
+        a.ptr(src.ptr); a.ptr(totals.ptr); a.i64(outer); a.i64(n); a.i64(inner); a.i64(chunk); a.i64(parts)
+        launch(ks["chunk_totals"], dev, _grid_1d(outer * parts * inner), 256, a)
+        a = Args()
+        a.ptr(totals.ptr); a.i64(outer); a.i64(inner); a.i64(parts)
+        launch(ks["chunk_offsets"], dev, _grid_1d(outer * inner), 256, a)
+        a = Args()
+        a.ptr(src.ptr); a.ptr(out.ptr); a.ptr(totals.ptr); a.i64(outer); a.i64(n); a.i64(inner)
+        a.i64(chunk); a.i64(parts)
+        launch(ks["chunk_final"], dev, _grid_1d(outer * parts * inner), 256, a)
+        return out
     if outer * inner >= 4096 or n < 65536:
         a = Args()
         a.ptr(src.ptr); a.ptr(out.ptr); a.i64(outer); a.i64(n); a.i64(inner)
@@ -473,4 +570,149 @@ def flatnonzero(mask):
     a.ptr(out.ptr); a.ptr(mask.ptr); a.ptr(pos.ptr); a.ptr(out.ptr); a.i64(mask.size); a.i64(1)
     a.scalar(2, np.int32)
     launch(ks["compact"], mask.dev, _grid(mask.size), 256, a)
+    return out
+
+
+# ------------------------------------------------------------------------------ argmax / argmin
+# (value, first index) pairs reduced in two phases over an (outer, n, inner) contiguous array.
+# NumPy's rules: the FIRST extreme element wins; a nan counts as the extreme.
+_ARG_SRC = r'''
+struct NAME_pair { T v; i64 i; };
+__device__ __forceinline__ bool NAME_isnan(T x) { return x != x; }
+// does a beat b?  (ISMAX is 1 for argmax, 0 for argmin)
+__device__ __forceinline__ bool NAME_beats(const NAME_pair& a, const NAME_pair& b) {
+  if (b.i < 0) return a.i >= 0;
+  if (a.i < 0) return false;
+  const bool an = NAME_isnan(a.v), bn = NAME_isnan(b.v);
+  if (an || bn) return an && (!bn || a.i < b.i);
+  if (a.v == b.v) return a.i < b.i;
+  return ISMAX ? a.v > b.v : a.v < b.v;
+}
+__device__ __forceinline__ NAME_pair NAME_shfl(NAME_pair p, int o) {
+  NAME_pair q;
+  q.v = dr_shfl_xor(p.v, o);
+  q.i = dr_shfl_xor(p.i, o);
+  return q;
+}
+// inner == 1: block (blockIdx.y = row, blockIdx.x = chunk of the row) -> one pair per (row, chunk)
+extern "C" __global__ void __launch_bounds__(256) NAME_rows(const T* __restrict__ in,
+    T* __restrict__ pv, i64* __restrict__ pi, i64 n, i64 chunk) {
+  __shared__ T sv[8];
+  __shared__ i64 si[8];
+  const i64 row = blockIdx.y, lo = (i64)blockIdx.x * chunk, hi = lo + chunk < n ? lo + chunk : n;
+  const T* p = in + row * n;
+  NAME_pair best; best.v = (T)0; best.i = -1;
+#pragma unroll 4
+  for (i64 k = lo + threadIdx.x; k < hi; k += 256) {
+    NAME_pair c; c.v = p[k]; c.i = k;
+    if (NAME_beats(c, best)) best = c;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { const NAME_pair q = NAME_shfl(best, o); if (NAME_beats(q, best)) best = q; }
+  if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = best.v; si[threadIdx.x >> 5] = best.i; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) { NAME_pair q; q.v = sv[w]; q.i = si[w]; if (NAME_beats(q, best)) best = q; }
+    pv[row * gridDim.x + blockIdx.x] = best.v;
+    pi[row * gridDim.x + blockIdx.x] = best.i;
+  }
+}
+// inner > 1: one thread per (outer, inner) element and chunk of n (blockIdx.y), coalesced along inner
+extern "C" __global__ void __launch_bounds__(256) NAME_cols(const T* __restrict__ in,
+    T* __restrict__ pv, i64* __restrict__ pi, i64 outer, i64 n, i64 inner, i64 chunk) {
+  const i64 total = outer * inner;
+  const i64 lo = (i64)blockIdx.y * chunk, hi = lo + chunk < n ? lo + chunk : n;
+  for (i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (i64)gridDim.x * blockDim.x) {
+    const i64 o = idx / inner, c = idx - o * inner;
+    const T* p = in + o * n * inner + c;
+    NAME_pair best; best.v = (T)0; best.i = -1;
+#pragma unroll 4
+    for (i64 k = lo; k < hi; ++k) {
+      NAME_pair q; q.v = p[k * inner]; q.i = k;
+      if (NAME_beats(q, best)) best = q;
+    }
+    pv[(o * gridDim.y + blockIdx.y) * inner + c] = best.v;
+    pi[(o * gridDim.y + blockIdx.y) * inner + c] = best.i;
+  }
+}
+// fold the `parts` partial pairs of every output element, in order
+extern "C" __global__ void __launch_bounds__(256) NAME_final(const T* __restrict__ pv,
+    const i64* __restrict__ pi, i64* __restrict__ out, i64 outer, i64 parts, i64 inner) {
+  const i64 total = outer * inner;
+  for (i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (i64)gridDim.x * blockDim.x) {
+    const i64 o = idx / inner, c = idx - o * inner;
+    NAME_pair best; best.v = (T)0; best.i = -1;
+    for (i64 s = 0; s < parts; ++s) {
+      NAME_pair q; q.v = pv[(o * parts + s) * inner + c]; q.i = pi[(o * parts + s) * inner + c];
+      if (NAME_beats(q, best)) best = q;
+    }
+    out[idx] = best.i;
+  }
+}
+'''
+
+
+def _arg_kernels(dt, is_max):
+    key = ("arg", np.dtype(dt).str, bool(is_max))
+    if key + ("rows",) in engine._kernels:
+        return {s: engine._kernels[key + (s,)] for s in ("rows", "cols", "final")}
+    name = engine.kernel_name(key)
+    T = ctype(dt) if np.dtype(dt) != np.dtype(bool) else "unsigned char"
+    src = _ARG_SRC.replace("NAME", name).replace("ISMAX", "1" if is_max else "0")
+    src = src.replace("(T)0", f"({T})0").replace("const T*", f"const {T}*").replace("T* ", f"{T}* ") \
+        .replace("T v;", f"{T} v;").replace("(T x)", f"({T} x)").replace("__shared__ T ", f"__shared__ {T} ")
+    _, cubin = engine.compile_source(name, src)
+    out = {}
+    for suffix in ("rows", "cols", "final"):
+        out[suffix] = engine._kernels[key + (suffix,)] = engine.Kernel(f"{name}_{suffix}", src, cubin, {})
+    return out
+
+
+def argreduce(src, axis, is_max):
+    """np.argmax / np.argmin of a DeviceArray along one axis (None: flattened); int64 result."""
+    src = src if src.is_contiguous else src.copy()
+    if axis is None:
+        outer, n, inner, out_shape = 1, src.size, 1, ()
+    else:
+        axis %= src.ndim
+        outer = int(np.prod(src.shape[:axis], dtype=np.int64))
+        n = src.shape[axis]
+        inner = int(np.prod(src.shape[axis + 1:], dtype=np.int64))
+        out_shape = tuple(src.shape[:axis]) + tuple(src.shape[axis + 1:])
+    if n == 0:
+        raise ValueError("attempt to get argmax of an empty sequence")
+    dev = src.dev
+    out = DeviceArray.empty(out_shape, np.int64, dev if dev >= 0 else None)
+    if out.size == 0:
+        return out
+    ks = _arg_kernels(src.dtype, is_max)
+    target = 148 * 8
+    if inner == 1:
+        parts = max(1, min(-(-target // outer), -(-n // 1024), 65535 if outer > 1 else 1 << 20))
+        chunk = -(-n // parts)
+        parts = -(-n // chunk)
+        rows_y = outer
+        if rows_y > 65535:                      # grid.y limit: fall back to the column kernel
+            inner, outer_c = 1, outer
+            parts, chunk = 1, n
+            pv = DeviceArray.empty((outer, 1), src.dtype, dev if dev >= 0 else None)
+            pi = DeviceArray.empty((outer, 1), np.int64, dev if dev >= 0 else None)
+            a = Args(); a.ptr(src.ptr); a.ptr(pv.ptr); a.ptr(pi.ptr); a.i64(outer_c); a.i64(n); a.i64(1); a.i64(chunk)
+            launch(ks["cols"], dev, (_grid(outer), 1, 1), 256, a)
+        else:
+            pv = DeviceArray.empty((outer, parts), src.dtype, dev if dev >= 0 else None)
+            pi = DeviceArray.empty((outer, parts), np.int64, dev if dev >= 0 else None)
+            a = Args(); a.ptr(src.ptr); a.ptr(pv.ptr); a.ptr(pi.ptr); a.i64(n); a.i64(chunk)
+            launch(ks["rows"], dev, (parts, rows_y, 1), 256, a)
+    else:
+        blocks_x = -(-(outer * inner) // 256)
+        parts = max(1, min(-(-target // blocks_x), n // 16 if n >= 32 else 1, 65535))
+        chunk = -(-n // parts)
+        parts = -(-n // chunk)
+        pv = DeviceArray.empty((outer, parts, inner), src.dtype, dev if dev >= 0 else None)
+        pi = DeviceArray.empty((outer, parts, inner), np.int64, dev if dev >= 0 else None)
+        a = Args(); a.ptr(src.ptr); a.ptr(pv.ptr); a.ptr(pi.ptr); a.i64(outer); a.i64(n); a.i64(inner); a.i64(chunk)
+        launch(ks["cols"], dev, (min(blocks_x, 148 * 16), parts, 1), 256, a)
+    a = Args(); a.ptr(pv.ptr); a.ptr(pi.ptr); a.ptr(out.ptr); a.i64(outer); a.i64(parts); a.i64(inner)
+    launch(ks["final"], dev, _grid(outer * inner), 256, a)
     return out

@@ -133,8 +133,8 @@ def split_operands(a_node, b_node):
     m, k = a_node.shape
     n = b_node.shape[1]
     f32 = np.dtype(np.float32)
-    a_node = a_node if a_node.dtype == f32 else a_node.astype(f32)
-    b_node = b_node if b_node.dtype == f32 else b_node.astype(f32)
+    from .delayarray import as_dtype
+    a_node, b_node = as_dtype(a_node, f32), as_dtype(b_node, f32)
     # hi = x rounded to TF32, lo = (x - hi) rounded to TF32: the tensor core then has nothing
     # left to truncate, so no biased error accumulates along K
     a_hi = RawOp("tf32_hi", a_node)
@@ -144,8 +144,13 @@ def split_operands(a_node, b_node):
     from .device import current_device
     dev = -1 if engine.is_dry() else current_device()
     kp = -(-k // 4) * 4                 # TMA wants row pitches that are multiples of 16 bytes
-    bufs = [DeviceArray.empty((rows, kp), f32, dev if dev >= 0 else None) for rows in (m, m, n, n)]
-    ah, al, bth, btl = (buf[:, :k] for buf in bufs)
+    # operands with fewer rows than one tile are padded with zero rows, so that a TMA box never
+    # exceeds the extent of its tensor map
+    bufs = [DeviceArray.empty((max(rows, BM), kp), f32, dev if dev >= 0 else None) for rows in (m, m, n, n)]
+    for buf, rows in zip(bufs, (m, m, n, n)):
+        if rows < BM and dev >= 0:
+            buf.fill(0)
+    ah, al, bth, btl = (buf[:rows, :k] for buf, rows in zip(bufs, (m, m, n, n)))
     engine.evaluate_nodes([a_hi, a_lo], outs=[ah, al])
     engine.evaluate_nodes([b_hi, b_lo], outs=[bth.T, btl.T])
     return ah, al, bth, btl
@@ -172,7 +177,7 @@ def matmul_tf32x3(a_node, b_node):
     kern = get_kernel(("tcgen05_gemm", BM, BN, BK, NS), lambda name: _SRC.replace("NAME", name))
     a = Args()
     for arr, rows in ((ah, m), (al, m), (bth, n), (btl, n)):
-        a.raw(_tensor_map(dev, arr, rows, k), 64)
+        a.raw(_tensor_map(dev, arr, max(rows, BM), k), 64)
     a.ptr(out.ptr)
     for v in (m, n, k):
         a.scalar(v, np.int32)

@@ -607,7 +607,8 @@ def test_fft_matches_numpy(gpu):
     np.testing.assert_allclose(lazy.get(), np.fft.fft(x * 2.0), rtol=1e-10, atol=1e-9)
 
 
-@pytest.mark.parametrize("shape", [(256, 192, 320), (1000, 777, 650), (128, 64, 128), (2048, 2048, 2048)])
+@pytest.mark.parametrize("shape", [(256, 192, 320), (1000, 777, 650), (128, 64, 128), (2048, 2048, 2048),
+                                   (1500, 300, 8), (4096, 1024, 64), (9, 200, 700), (130, 64, 17)])
 def test_dense_matmul_tcgen05(gpu, shape):
     """A genuine dense float32 `@` runs on the tensor cores (tcgen05, 3xTF32 split) and must still
     meet the fp32 bar: |C - C_exact| <= 1e-5 * (|A| @ |B|), the usual matmul tolerance."""
@@ -685,3 +686,108 @@ def test_reductions_of_empty_arrays_follow_numpy(gpu):
     assert np.array_equal(np.sum(z, axis=0).get(), np.zeros(5, np.float32))
     assert np.array_equal(np.prod(z, axis=0).get(), np.ones(5, np.float32))
     assert np.sum(z, axis=1).get().shape == (0,)
+
+
+# ------------------------------------------------------------------ axis kernels, second generation
+@pytest.mark.parametrize("dt", [np.float32, np.float64, np.int32])
+def test_axis_reductions_vector_split_and_transposed_paths(gpu, dt):
+    """rows / cols kernels with 128-bit loads, a split reduced axis (partials folded in fixed
+    order), and the transposed dispatch (`v @ X`, reductions of X.T); integer results exact,
+    float sums within the reduction bar, max/min exact."""
+    rng = np.random.default_rng(71)
+    scale = [1.0]       # the bar is relative to the sum of magnitudes (NumPy's own float32 row-by-
+    #                     row accumulation is ~1e-5 of that away from the exact sum)
+
+    def check(got, want, what):
+        tol = dict(rtol=1e-12, atol=1e-12 * scale[0]) if dt == np.float64 else dict(rtol=1e-5, atol=1e-5 * scale[0])
+        got = got.get()
+        assert got.shape == want.shape and got.dtype == want.dtype, (what, got.dtype, want.dtype)
+        if dt == np.int32 or "max" in what or "min" in what:
+            assert np.array_equal(got, want), what
+        else:
+            np.testing.assert_allclose(got, want, err_msg=what, **tol)
+
+    for shape in ((2048, 512), (4099, 260), (515, 1028), (64, 5000), (7, 100003), (30000, 12)):
+        x = (rng.standard_normal(shape) * 20).astype(dt)
+        X = gpu.array(x)
+        scale[0] = float(np.abs(x).max()) ** 2 * max(shape)
+        v0 = (rng.standard_normal(shape[0]) * 3).astype(dt)
+        v1 = (rng.standard_normal(shape[1]) * 3).astype(dt)
+        check(np.sum(X, axis=0), np.sum(x, axis=0), f"sum0 {shape}")
+        check(np.sum(X, axis=1), np.sum(x, axis=1), f"sum1 {shape}")
+        check(np.max(X, axis=0), np.max(x, axis=0), f"max0 {shape}")
+        check(np.min(X, axis=1), np.min(x, axis=1), f"min1 {shape}")
+        check(np.sum(X.T, axis=1), np.sum(x.T, axis=1), f"sumT1 {shape}")
+        check(np.max(X.T, axis=0), np.max(x.T, axis=0), f"maxT0 {shape}")
+        check(X @ gpu.array(v1), x @ v1, f"X@v {shape}")
+        check(gpu.array(v0) @ X, v0 @ x, f"v@X {shape}")
+        check(np.sum(X[1:, 1:], axis=0), np.sum(x[1:, 1:], axis=0), f"sum0 offset {shape}")
+        check(np.sum(X[:, ::2], axis=1), np.sum(x[:, ::2], axis=1), f"sum1 strided {shape}")
+        check(np.sum(X * gpu.array(v1)[None, :], axis=0), np.sum(x * v1[None, :], axis=0), f"sum0 bcast {shape}")
+        check(np.sum(X * gpu.array(v0)[:, None], axis=1), np.sum(x * v0[:, None], axis=1), f"sum1 bcast {shape}")
+        if dt != np.int32:
+            check(np.mean(X * X, axis=0), np.mean(x * x, axis=0), f"mean0 {shape}")
+            np.testing.assert_allclose(np.var(X, axis=0).get(), np.var(x, axis=0), rtol=1e-4 if dt == np.float32 else 1e-10)
+    c = (rng.standard_normal((6, 4100, 36)) * 5).astype(dt)
+    scale[0] = float(np.abs(c).max()) * 4100
+    check(np.sum(gpu.array(c), axis=1), np.sum(c, axis=1), "middle axis")
+    check(np.max(gpu.array(c), axis=1), np.max(c, axis=1), "middle axis max")
+
+
+def test_argmax_argmin_pair_reduction(gpu):
+    rng = np.random.default_rng(72)
+    for dt in (np.float32, np.float64, np.int32, np.int64, np.uint8, np.bool_):
+        for shape in ((1,), (100003,), (3_000_001,), (513, 1030), (6, 4100, 36), (70000, 3)):
+            x = (rng.standard_normal(shape) * 50).astype(dt)       # small dtypes: many ties
+            X = gpu.array(x)
+            for ax in (None,) + tuple(range(len(shape))):
+                for fn in (np.argmax, np.argmin):
+                    got = fn(X, axis=ax).get()
+                    want = fn(x, axis=ax)
+                    assert got.shape == np.shape(want) and np.array_equal(got, want), (dt, shape, ax, fn.__name__)
+    x = rng.standard_normal(5000)
+    x[[77, 4000]] = np.nan                                         # first nan wins, like NumPy
+    assert int(np.argmax(gpu.array(x))) == 77 and int(np.argmin(gpu.array(x))) == 77
+    m = rng.standard_normal((300, 40)); m[200, 7] = np.nan; m[100, 7] = np.nan
+    assert np.array_equal(np.argmax(gpu.array(m), axis=0).get(), np.argmax(m, axis=0))
+    assert np.array_equal(np.argmin(gpu.array(m), axis=1, keepdims=True).get(), np.argmin(m, axis=1, keepdims=True))
+    assert int(np.argmax(gpu.array(x) * 2.0 + 1.0)) == 77        # lazy producer is forced first
+    with pytest.raises(ValueError):
+        np.argmax(gpu.array(np.zeros(0)))
+
+
+def test_cumsum_row_scan_and_chunked_axis_scan(gpu):
+    rng = np.random.default_rng(73)
+    for shape in ((300, 5000), (64, 64), (1000, 2049), (5000, 300), (3, 70000, 5), (9, 40, 1000)):
+        xi = rng.integers(-100, 100, shape)
+        xf = rng.standard_normal(shape)
+        for ax in range(len(shape)):
+            assert_bits_equal(np.cumsum(gpu.array(xi), axis=ax).get(), np.cumsum(xi, axis=ax), f"int cumsum {shape} {ax}")
+            np.testing.assert_allclose(np.cumsum(gpu.array(xf), axis=ax).get(), np.cumsum(xf, axis=ax),
+                                       rtol=1e-11, atol=1e-9, err_msg=f"{shape} {ax}")
+        x32 = xf.astype(np.float32)
+        np.testing.assert_allclose(np.cumsum(gpu.array(x32), axis=-1).get(), np.cumsum(x32, axis=-1), rtol=1e-4, atol=1e-2)
+    b = rng.integers(0, 2, (200, 3000)).astype(bool)
+    assert_bits_equal(np.cumsum(gpu.array(b), axis=1).get(), np.cumsum(b, axis=1), "bool cumsum rows")
+
+
+def test_internal_casts_never_convert_the_users_leaf(gpu):
+    """`leaf.astype` is in place (reference delayarray.py:401-408), so promotions inside
+    reductions, contractions and dtype= arguments must go through a cast NODE: an int32 array is
+    still int32 after it has been summed (found by the second-generation axis tests)."""
+    xi = np.arange(12, dtype=np.int32).reshape(3, 4)
+    X = gpu.array(xi)
+    v = gpu.array(np.ones(4, dtype=np.float64))
+    for use in (lambda: np.sum(X).get(), lambda: np.sum(X, axis=0).get(), lambda: np.mean(X).get(),
+                lambda: np.sum(X, dtype=np.float32).get(), lambda: np.cumsum(X, dtype=np.float64).get(),
+                lambda: (X @ v).get(), lambda: (X @ gpu.array(np.ones((4, 2), np.float32))).get(),
+                lambda: np.var(X, dtype=np.float64).get(), lambda: np.add(X, 1, dtype=np.float64).get()):
+        use()
+        assert X.dtype == np.int32 and X.get().dtype == np.int32
+    b = gpu.array(xi > 5)
+    assert int(np.sum(b)) == 6 and b.dtype == np.bool_
+    assert np.max(X, axis=0).get().dtype == np.int32
+    f = gpu.array(np.ones((130, 64), np.float64))
+    (f @ gpu.array(np.ones((64, 130), np.float32))).get()
+    assert f.dtype == np.float64
+    assert X.astype(np.float32) is X and X.dtype == np.float32          # the user-facing call IS in place
