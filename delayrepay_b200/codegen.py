@@ -1019,6 +1019,8 @@ def gen_stencil(name, prog, roles, out_dt, TW=248, TH=32, NS=4, threads=992):
     assert BW <= 256 and BH <= 256
     stage_bytes = BW * BH * np.dtype(out_dt).itemsize
     stage_bytes_al = -(-stage_bytes // 128) * 128
+    # the ring must fit the 227 KB of one SM: float64 boxes are twice as large (3 stages)
+    NS = max(2, min(NS, (216 * 1024) // stage_bytes_al))
     cols_per_row = TW // V                          # threads along x
     rows_per_pass = threads // cols_per_row
     in_class = tuple("b" if r[0] == "b" else "c" for r in roles)

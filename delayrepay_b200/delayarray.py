@@ -85,6 +85,10 @@ class Memoiser(type):
         if key is None:
             return super().__call__(*args, **kwargs)
         hit = Memoiser._cache.get(key)
+        if hit is not None and hit.__dict__.get("array") is not None and not _stamp_valid(hit._stamp):
+            # evaluated before one of its inputs was written: that node keeps ITS value (whoever
+            # holds it sees a snapshot, as with NumPy); this new capture must see the new data
+            hit = None
         if hit is None:
             hit = super().__call__(*args, **kwargs)
             Memoiser._cache[key] = hit
@@ -128,10 +132,12 @@ class DelayArray(numpy.lib.mixins.NDArrayOperatorsMixin):
 
     # ---- forcing points  [delayarray.py:35-44,101-112]
     def _force(self):
-        """Evaluate (once) and return the backend array; re-evaluates when a buffer this
-        result was computed from has been written since (buffer version counters)."""
+        """Evaluate ONCE and return the backend array (reference delayarray.py:38-44: cached in
+        self.array).  An evaluated node is a snapshot: later writes to its inputs do not change
+        it; capturing the same expression again after such a write yields a fresh node
+        (Memoiser.__call__ checks the buffer version counters)."""
         arr = self.__dict__.get("array")
-        if arr is not None and _stamp_valid(self._stamp):
+        if arr is not None:
             return arr
         self.array = _backend.run(self)
         return self.array

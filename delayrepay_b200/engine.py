@@ -524,10 +524,9 @@ def run(node):
 
 def run_many(nodes):
     """Co-evaluate: elementwise nodes sharing a shape go into ONE multi-output kernel."""
-    from .delayarray import _stamp_valid
     groups = {}
     for n in nodes:
-        if n.kind == "ewise" and not (n.__dict__.get("array") is not None and _stamp_valid(n._stamp)):
+        if n.kind == "ewise" and n.__dict__.get("array") is None:
             groups.setdefault(tuple(n.shape), [])
             if all(n is not m for m in groups[tuple(n.shape)]):
                 groups[tuple(n.shape)].append(n)

@@ -59,8 +59,9 @@ class Program:
 
 
 def _is_materialised(node):
-    from .delayarray import _stamp_valid
-    return node.__dict__.get("array") is not None and _stamp_valid(node._stamp)
+    # an evaluated node is a snapshot (DelayArray._force): its array is what its consumers read,
+    # whether or not its inputs have been written since
+    return node.__dict__.get("array") is not None
 
 
 def build_program(roots):

@@ -433,6 +433,25 @@ def test_heat_bit_exact(gpu, shape, steps):
         assert_bits_equal(u.get(), GOLDEN["heat"], "heat golden")
 
 
+def test_heat_float64_and_general_shifted_assignments(gpu):
+    """The stencil kernel for 8-byte cells (3-stage ring: a float64 box is twice as large) and for
+    right-hand sides that are not the heat update (found by tools/fuzz_state.py)."""
+    rng = np.random.default_rng(44)
+    for shape in ((130, 300), (33, 256), (4, 300), (1000, 1031)):
+        u0 = rng.random(shape)
+        u = gpu.array(u0.copy())
+        wl.heat(gpu, u, 3)
+        assert_bits_equal(u.get(), wl.heat(refcpu, refcpu.leaf(u0.copy()), 3).get(), f"heat float64 {shape}")
+        a, b = u0.copy(), rng.random(shape)
+        A, B = gpu.array(a), gpu.array(b)
+        a[:, 2:-2] = np.maximum((a[:, 3:-1] + b[:, 2:-2]) * 0.5, 1.5 * b[:, 1:-3])
+        A[:, 2:-2] = np.maximum((A[:, 3:-1] + B[:, 2:-2]) * 0.5, 1.5 * B[:, 1:-3])
+        assert_bits_equal(A.get(), a, f"shifted max {shape}")
+        a[1:-1, :] = np.where(a[2:, :] > a[:-2, :], a[1:-1, :], b[1:-1, :] * 0.5)
+        A[1:-1, :] = np.where(A[2:, :] > A[:-2, :], A[1:-1, :], B[1:-1, :] * 0.5)
+        assert_bits_equal(A.get(), a, f"shifted where {shape}")
+
+
 def test_heat_steps_reuse_one_kernel(gpu):
     from delayrepay_b200 import engine
     u = gpu.array(wl.make_inputs("heat", 96)["u"])
