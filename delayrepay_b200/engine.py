@@ -1161,6 +1161,10 @@ def materialize_view(arr):
         pairs = DeviceArray(arr.buf, arr.shape + (2,), part, arr.strides + (part.itemsize,), arr.offset)
         flat = materialize_view(pairs)
         return DeviceArray(flat.buf, arr.shape, arr.dtype, None, flat.offset)
+    from . import extras
+    fast = extras.transpose_copy(arr)            # X.T.copy(): tiled shared-memory transpose
+    if fast is not None:
+        return fast
     outs, _ = evaluate_nodes([NPArray(arr)])
     return outs[0]
 

@@ -716,3 +716,86 @@ def argreduce(src, axis, is_max):
     a = Args(); a.ptr(pv.ptr); a.ptr(pi.ptr); a.ptr(out.ptr); a.i64(outer); a.i64(parts); a.i64(inner)
     launch(ks["final"], dev, _grid(outer * inner), 256, a)
     return out
+
+
+# ------------------------------------------------------------------------------ transpose
+# out[b, c, r] = in[b, r, c] through 32 x 33 shared-memory tiles: both the loads and the stores
+# are coalesced (the index-decomposing `nd` kernel reads a transposed view a row pitch apart).
+_TRANSPOSE_SRC = r'''
+// tile = 32 source rows x TC source columns (TC = 64 for 4-byte words: 8 independent loads per
+// thread, the same bytes in flight as 8-byte words with TC = 32)
+#define TC TCVAL
+extern "C" __global__ void __launch_bounds__(256) NAME(const W* __restrict__ in, W* __restrict__ out,
+    i64 rows, i64 cols, i64 in_pitch, i64 out_pitch, i64 in_batch, i64 out_batch, i64 tiles_x, i64 tiles_y,
+    i64 ntiles) {
+  __shared__ W tile[32][TC + 1];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8 threads
+  for (i64 t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const i64 b = t / (tiles_x * tiles_y), rem = t - b * tiles_x * tiles_y;
+    const i64 by = rem / tiles_x, bx = rem - by * tiles_x;
+    const W* src = in + b * in_batch;
+    W* dst = out + b * out_batch;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const i64 r = by * 32 + ty + k * 8;
+#pragma unroll
+      for (int j = 0; j < TC / 32; ++j) {
+        const i64 c = bx * TC + tx + j * 32;
+        if (r < rows && c < cols) tile[ty + k * 8][tx + j * 32] = src[r * in_pitch + c];
+      }
+    }
+    __syncthreads();
+    const i64 oc = by * 32 + tx;                                   // output column = input row
+#pragma unroll
+    for (int k = 0; k < TC / 8; ++k) {
+      const i64 orow = bx * TC + ty + k * 8;                       // output row = input column
+      if (orow < cols && oc < rows) dst[orow * out_pitch + oc] = tile[tx][ty + k * 8];
+    }
+    __syncthreads();
+  }
+}
+'''
+
+
+def transposed_source(arr):
+    """If `arr` (ndim >= 2) is exactly the last-two-axes transpose of a C-contiguous array, return
+    (batch, rows, cols) of that source, else None."""
+    if arr.ndim < 2 or arr.dtype.itemsize not in (4, 8) or arr.size == 0:
+        return None
+    item = arr.dtype.itemsize
+    n_r, n_c = arr.shape[-1], arr.shape[-2]                        # source is (.., n_r, n_c)
+    if arr.strides[-2] != item or n_r < 32 or n_c < 32:
+        return None
+    if arr.ndim == 2 and arr.strides[-1] % item == 0 and arr.strides[-1] >= n_c * item:
+        return 1, n_r, n_c                                         # a column block of a matrix: pitch > n_c
+    if arr.strides[-1] != n_c * item:
+        return None
+    batch, pitch = 1, n_r * n_c * item
+    for n, st in zip(reversed(arr.shape[:-2]), reversed(arr.strides[:-2])):
+        if n != 1 and st != pitch:
+            return None
+        pitch *= n
+        batch *= n
+    return batch, n_r, n_c
+
+
+def transpose_copy(arr, out=None):
+    """C-contiguous copy of a transposed view (see transposed_source); None if not applicable."""
+    info = transposed_source(arr)
+    if info is None:
+        return None
+    batch, rows, cols = info                                       # source (batch, rows, cols)
+    item = arr.dtype.itemsize
+    if out is None:
+        out = DeviceArray.empty(arr.shape, arr.dtype, arr.dev if arr.dev >= 0 else None)
+    key = ("transpose", item)
+    tc = 64 if item == 4 else 32
+    kern = get_kernel(key, lambda name: _TRANSPOSE_SRC.replace("NAME", name).replace("TCVAL", str(tc))
+                      .replace("W", _WORD[item]))
+    tiles_x, tiles_y = -(-cols // tc), -(-rows // 32)
+    ntiles = batch * tiles_x * tiles_y
+    a = Args()
+    a.ptr(arr.ptr); a.ptr(out.ptr); a.i64(rows); a.i64(cols); a.i64(arr.strides[-1] // item); a.i64(rows)
+    a.i64(rows * cols); a.i64(rows * cols); a.i64(tiles_x); a.i64(tiles_y); a.i64(ntiles)
+    launch(kern, arr.dev, max(1, min(ntiles, 148 * 16)), 256, a)
+    return out

@@ -152,7 +152,23 @@ def split_operands(a_node, b_node):
             buf.fill(0)
     ah, al, bth, btl = (buf[:rows, :k] for buf, rows in zip(bufs, (m, m, n, n)))
     engine.evaluate_nodes([a_hi, a_lo], outs=[ah, al])
-    engine.evaluate_nodes([b_hi, b_lo], outs=[bth.T, btl.T])
+    from . import extras
+    from .delayarray import NPArray
+    b_t = None
+    if b_node.dtype == f32 and min(k, n) >= 32:
+        # transpose B once through shared-memory tiles (coalesced both ways), then split B^T
+        # with contiguous stores; writing hi/lo straight into transposed outputs stores 4-byte
+        # words a row pitch apart
+        b_dev = b_node._force()
+        b_dev = b_dev if b_dev.is_contiguous else b_dev.copy()
+        b_t = extras.transpose_copy(b_dev.T)
+    if b_t is not None:
+        bt_node = NPArray(b_t)
+        bt_hi = RawOp("tf32_hi", bt_node)
+        bt_lo = RawOp("tf32_hi", BinaryNumpyEx(np.subtract, bt_node, bt_hi))
+        engine.evaluate_nodes([bt_hi, bt_lo], outs=[bth, btl])
+    else:
+        engine.evaluate_nodes([b_hi, b_lo], outs=[bth.T, btl.T])
     return ah, al, bth, btl
 
 

@@ -209,3 +209,21 @@ def test_integer_array_and_boolean_mask_indexing(gpu):
     with pytest.raises(IndexError):
         gpu.array(np.arange(6.0))[gpu.array(np.array([True, False]))]
     assert gpu.array(np.arange(5.0))[gpu.array(np.zeros(0, dtype=np.int64))].get().shape == (0,)
+
+
+def test_transposed_copies_use_the_tiled_kernel_and_are_exact(gpu):
+    from delayrepay_b200 import engine
+    rng = np.random.default_rng(21)
+    for dt in (np.float32, np.float64, np.int32, np.int64):
+        for shape in ((33, 65), (256, 512), (1000, 37), (3, 64, 96), (2, 3, 40, 50)):
+            x = (rng.standard_normal(shape) * 100).astype(dt)
+            X = gpu.array(x)
+            t = np.swapaxes(X, -1, -2)
+            assert np.array_equal(t.copy().get(), np.swapaxes(x, -1, -2).copy())
+            assert np.array_equal(t.reshape(-1).get(), np.swapaxes(x, -1, -2).reshape(-1))
+        m = (rng.standard_normal((300, 400)) * 100).astype(dt)
+        M = gpu.array(m)
+        assert np.array_equal(M[:, 17:250].T.copy().get(), m[:, 17:250].T.copy())      # pitch > width
+        assert np.array_equal(M[5:, :].T.copy().get(), m[5:, :].T.copy())
+        assert np.array_equal(M[::2, :].T.copy().get(), m[::2, :].T.copy())            # not a transpose: nd path
+    assert any(k[0] == "transpose" for k in engine._kernels), "tiled transpose not taken"

@@ -55,6 +55,7 @@ for dt, w in ((np.float32, 4), (np.float64, 8)):
     report(f"cumsum(X, axis=0) {t}", 2 * N * w, lambda: np.cumsum(X, axis=0).run())
     report(f"cumsum(X, axis=1) {t}", 2 * N * w, lambda: np.cumsum(X, axis=1).run())
     report(f"X.T.copy() {t}", 2 * N * w, lambda: X.T.copy())
+    report(f"X.T.reshape(-1) {t}", 2 * N * w, lambda: X.T.reshape(-1))
     report(f"X.T + X {t}", 3 * N * w, lambda: (X.T + X).run())
     report(f"X[:, ::2] * 2 {t}", N * w, lambda: (X[:, ::2] * 2.0).run())
     report(f"concatenate([X, X]) {t}", 4 * N * w, lambda: np.concatenate([X, X]))
