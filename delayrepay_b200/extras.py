@@ -401,6 +401,73 @@ extern "C" __global__ void __launch_bounds__(256) NAME_compact(W* __restrict__ s
     else out[o] = (W)i;
   }
 }
+// ---- element masks (inner == 1) without a position array: tiles of 4096 mask bytes
+// (1) per-tile counts, (2) exclusive scan of the counts (scan kernels), (3) per-tile scatter:
+// every thread owns 16 consecutive mask bytes (one 128-bit load when aligned), its rank inside
+// the tile comes from warp shuffles + 8 warp totals, the tile's base from the scanned counts.
+__device__ __forceinline__ unsigned NAME_flags16(const unsigned char* __restrict__ mask, i64 first, i64 n) {
+  unsigned bits = 0;
+  if (first + 16 <= n && ((unsigned long long)(mask + first) & 15ull) == 0) {
+    const uint4 v = *reinterpret_cast<const uint4*>(mask + first);
+    const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      unsigned x = w[q];
+      x |= x >> 4; x |= x >> 2; x |= x >> 1; x &= 0x01010101u;          // byte != 0 -> bit 0 of the byte
+      bits |= ((x & 1u) | ((x >> 7) & 2u) | ((x >> 14) & 4u) | ((x >> 21) & 8u)) << (4 * q);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) if (first + j < n && mask[first + j]) bits |= 1u << j;
+  }
+  return bits;
+}
+extern "C" __global__ void __launch_bounds__(256) NAME_mcount(const unsigned char* __restrict__ mask,
+    i64* __restrict__ counts, i64 n, i64 ntiles) {
+  __shared__ int warp_tot[8];
+  if (blockIdx.x == 0 && threadIdx.x == 0) counts[ntiles] = 0;    // slot of the grand total
+  for (i64 t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    int c = __popc(NAME_flags16(mask, t * 4096 + (i64)threadIdx.x * 16, n));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0) warp_tot[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int s = 0;
+      for (int w = 0; w < 8; ++w) s += warp_tot[w];
+      counts[t] = s;
+    }
+    __syncthreads();
+  }
+}
+// mode 0: out[rank] = data[i]   1: data[i] = out[rank]   2: out[rank] = i
+extern "C" __global__ void __launch_bounds__(256) NAME_mscatter(W* __restrict__ data,
+    const unsigned char* __restrict__ mask, const i64* __restrict__ offsets, W* __restrict__ out,
+    i64 n, i64 ntiles, int mode) {
+  __shared__ int warp_tot[8];
+  for (i64 t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const i64 first = t * 4096 + (i64)threadIdx.x * 16;
+    const unsigned bits = NAME_flags16(mask, first, n);
+    const int c = __popc(bits);
+    int x = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if ((threadIdx.x & 31) >= o) x += y; }
+    if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = x;
+    __syncthreads();
+    i64 rank = offsets[t] + (x - c);
+    for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) rank += warp_tot[w];
+    unsigned rest = bits;
+    while (rest) {
+      const int j = __ffs(rest) - 1;
+      rest &= rest - 1;
+      if (mode == 0) out[rank] = data[first + j];
+      else if (mode == 1) data[first + j] = out[rank];
+      else out[rank] = (W)(first + j);
+      ++rank;
+    }
+    __syncthreads();
+  }
+}
 '''
 _WORD = {1: "unsigned char", 2: "unsigned short", 4: "unsigned int", 8: "unsigned long long"}
 
@@ -408,13 +475,14 @@ _WORD = {1: "unsigned char", 2: "unsigned short", 4: "unsigned int", 8: "unsigne
 def _index_kernels(itemsize, idx_dt):
     key = ("index", itemsize, np.dtype(idx_dt).str)
     if key + ("take",) in engine._kernels:
-        return {suffix: engine._kernels[key + (suffix,)] for suffix in ("take", "put", "compact")}
+        return {suffix: engine._kernels[key + (suffix,)]
+                for suffix in ("take", "put", "compact", "mcount", "mscatter")}
     name = engine.kernel_name(key)
     src = _INDEX_SRC.replace("NAME", name).replace("IDX", ctype(idx_dt))
     src = src.replace("W*", _WORD[itemsize] + "*").replace("(W)", f"({_WORD[itemsize]})")
     _, cubin = engine.compile_source(name, src)
     out = {}
-    for suffix in ("take", "put", "compact"):
+    for suffix in ("take", "put", "compact", "mcount", "mscatter"):
         k = engine._kernels.get(key + (suffix,))
         if k is None:
             k = engine._kernels[key + (suffix,)] = engine.Kernel(f"{name}_{suffix}", src, cubin, {})
@@ -517,10 +585,40 @@ def _mask_positions(mask):
     return mask, pos, count
 
 
+def _mask_tiles(mask, itemsize):
+    """Element masks: per-tile counts scanned in place -> (mask, offsets, count, ntiles, kernels).
+    offsets[t] = number of set elements before tile t (tiles of 4096), offsets[ntiles] = total."""
+    mask = mask if mask.is_contiguous else mask.copy()
+    n = mask.size
+    ntiles = -(-n // 4096)
+    dev = mask.dev
+    ks = _index_kernels(itemsize, np.int64)
+    counts = DeviceArray.empty((ntiles + 1,), np.int64, dev if dev >= 0 else None)
+    a = Args(); a.ptr(mask.ptr); a.ptr(counts.ptr); a.i64(n); a.i64(ntiles)
+    launch(ks["mcount"], dev, max(1, min(ntiles, 148 * 8)), 256, a)
+    a = Args(); a.ptr(counts.ptr); a.scalar(ntiles + 1, np.int32)
+    launch(_scan_kernels(np.int64, np.int64)["offsets"], dev, 1, 1024, a)
+    count = int(counts[ntiles:].get()[0]) if dev >= 0 else 0
+    return mask, counts, count, ntiles, ks
+
+
+def _mask_scatter(ks, data, mask, offsets, out, n, ntiles, mode):
+    a = Args()
+    a.ptr(data.ptr); a.ptr(mask.ptr); a.ptr(offsets.ptr); a.ptr(out.ptr); a.i64(n); a.i64(ntiles)
+    a.scalar(mode, np.int32)
+    launch(ks["mscatter"], mask.dev, max(1, min(ntiles, 148 * 8)), 256, a)
+
+
 def compress(src, mask):
     """src[mask] for a boolean DeviceArray covering the leading dimensions of src."""
     src = src if src.is_contiguous else src.copy()
     rows, inner = _mask_layout(src, mask)
+    if inner == 1 and rows > 0:
+        mask, offsets, count, ntiles, ks = _mask_tiles(mask, _word_size(src.dtype))
+        out = DeviceArray.empty((count,), src.dtype, src.dev if src.dev >= 0 else None)
+        if count or src.dev < 0:
+            _mask_scatter(ks, src, mask, offsets, out, rows, ntiles, 0)
+        return out
     mask, pos, count = _mask_positions(mask)
     out = DeviceArray.empty((count,) + tuple(src.shape[mask.ndim:]), src.dtype, src.dev if src.dev >= 0 else None)
     if out.size == 0 and src.dev >= 0:
@@ -538,7 +636,11 @@ def put_mask(dst, mask, vals):
     if not dst.is_contiguous:
         raise NotImplementedError("masked assignment of an array into a non-contiguous view")
     rows, inner = _mask_layout(dst, mask)
-    mask, pos, count = _mask_positions(mask)
+    fused = inner == 1 and rows > 0
+    if fused:
+        mask, pos, count, ntiles, fks = _mask_tiles(mask, _word_size(dst.dtype))
+    else:
+        mask, pos, count = _mask_positions(mask)
     want = (count,) + tuple(dst.shape[mask.ndim:])
     vals = vals.astype(dst.dtype) if vals.dtype != dst.dtype else vals
     if tuple(vals.shape) != want:
@@ -551,6 +653,10 @@ def put_mask(dst, mask, vals):
     vals = vals if vals.is_contiguous else vals.copy()
     if count == 0 and dst.dev >= 0:
         return
+    if fused:
+        _mask_scatter(fks, dst, mask, pos, vals, rows, ntiles, 1)
+        dst.buf.version += 1
+        return
     ks = _index_kernels(_word_size(dst.dtype), np.int64)
     a = Args()
     a.ptr(dst.ptr); a.ptr(mask.ptr); a.ptr(pos.ptr); a.ptr(vals.ptr); a.i64(rows); a.i64(inner)
@@ -561,6 +667,12 @@ def put_mask(dst, mask, vals):
 
 def flatnonzero(mask):
     """Indices (int64) of the set elements of a boolean DeviceArray, flattened, ascending."""
+    if mask.size:
+        mask, offsets, count, ntiles, ks = _mask_tiles(mask, 8)
+        out = DeviceArray.empty((count,), np.int64, mask.dev if mask.dev >= 0 else None)
+        if count or mask.dev < 0:
+            _mask_scatter(ks, out, mask, offsets, out, mask.size, ntiles, 2)
+        return out
     mask, pos, count = _mask_positions(mask)
     out = DeviceArray.empty((count,), np.int64, mask.dev if mask.dev >= 0 else None)
     if count == 0 and mask.dev >= 0:
