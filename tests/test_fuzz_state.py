@@ -21,7 +21,6 @@ def test_random_statement_programs_plan_and_compile_without_a_device():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("first", [0, 200])
-def test_random_statement_programs_match_numpy(gpu, first):
-    bad = [m for m in (fuzz_state.run_one(s) for s in range(first, first + 200)) if m]
+def test_random_statement_programs_match_numpy(gpu):
+    bad = [m for m in (fuzz_state.run_one(s) for s in range(200)) if m]
     assert not bad, "\n".join(bad)
