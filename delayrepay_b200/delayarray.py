@@ -994,7 +994,20 @@ def create_ex(func, args):
         return UnaryFuncEx(func, *args)
     if name == "power":
         return pow_ex(func, *args)
+    if name in _COMPARISONS:
+        # NumPy 2 compares an integer array with an out-of-range Python int by value
+        # (`uint8_array <= -3` is all False, no OverflowError): give such a scalar a 64-bit type
+        args = list(args)
+        for i, (a, other) in enumerate(zip(args, reversed(args))):
+            if isinstance(a, Scalar) and a.weak_type is int and other.dtype is not None \
+                    and other.dtype.kind in "iu":
+                info = np.iinfo(other.dtype)
+                if not info.min <= a.val <= info.max:
+                    args[i] = Scalar(np.int64(a.val) if a.val < 2 ** 63 else np.uint64(a.val))
     return BinaryFuncEx(func, *args)
+
+
+_COMPARISONS = {"greater", "greater_equal", "less", "less_equal", "equal", "not_equal"}
 
 
 # --------------------------------------------------------------------------- __array_function__

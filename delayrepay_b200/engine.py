@@ -479,6 +479,61 @@ def _plan_record(key, ops, prog, outs, rec):
     _plans[key] = p
 
 
+def _reduce_plan_key(src, op, res_dt, post):
+    from .delayarray import _leaf_sig
+    if src.kind == "leaf":
+        sig = _leaf_sig(src)
+        if sig is None:
+            return None, None
+        return ("reduce", "leaf", sig, op, res_dt.str, post), (src,)
+    d = src.__dict__
+    sig = d.get("_psig")
+    if src.kind != "ewise" or sig is None:
+        return None, None
+    return ("reduce", sig, src.shape, src.dtype, op, res_dt.str, post), d["_pops"]
+
+
+def _reduce_plan_launch(plan, ops, shape, res_dt, post):
+    """_plan_launch for a fused full reduction: operands, then the partials / ticket / result
+    pointers and the post scale (run_program's argument order)."""
+    from .delayarray import _leaf_sig
+    arrays = []
+    for i, want in zip(plan.arr_idx, plan.leaf_sigs):
+        leaf = ops[i]
+        if _leaf_sig(leaf) != want:
+            return None
+        arrays.append(leaf._force())
+    if plan.scl is not None:
+        for j, (i, dt) in enumerate(zip(plan.sc_idx, plan.sc_dt)):
+            if ranges.scalar_class(ops[i].val, dt) != plan.scl[j]:
+                return None
+    dev = plan.dev
+    st = dev_state(dev)
+    result = DeviceArray.empty(shape, res_dt, dev if dev >= 0 else None)
+    a = Args()
+    if plan.head[0] == "i64":
+        a.i64(plan.head[1])
+    else:
+        a.raw(plan.head[1], 8)
+    for arr in arrays:
+        a.ptr(arr.ptr)
+    for i, dt in zip(plan.sc_idx, plan.sc_dt):
+        a.scalar(ops[i].val, dt)
+    a.ptr(st.partials_ptr)
+    a.ptr(st.counter_ptr)
+    a.ptr(result.ptr)
+    a.f64(post)
+    launch(plan.kern, dev, plan.grid, plan.threads, a, smem=plan.smem)
+    seen, stamp = set(), []
+    for arr in arrays:
+        b = arr.buf
+        if id(b) not in seen:
+            seen.add(id(b))
+            stamp.append((weakref.ref(b), b.version))
+    stats["plan_hits"] = stats.get("plan_hits", 0) + 1
+    return result, stamp
+
+
 def evaluate_nodes(nodes, outs=None, inplace=False):
     """Fuse ``nodes`` (same iteration shape) into one kernel; returns the output arrays."""
     key = ops = None
@@ -588,6 +643,17 @@ def _run_reduce(node):
             from .delayarray import as_dtype
             res = as_dtype(NPArray(res) / float(count), res_dt)._force()
         return res.reshape(node.shape)
+    rkey = rops = None
+    if _PLAN_CACHE and full and axes and child.size:
+        # prepared launches for full reductions: the producer's structural signature (or the
+        # leaf's layout) + the reduction; a hit packs pointers and launches, nothing else
+        rkey, rops = _reduce_plan_key(src, op, res_dt, node.post)
+        plan = _plans.get(rkey) if rkey is not None else None
+        if plan is not None:
+            done = _reduce_plan_launch(plan, rops, node.shape, res_dt, post)
+            if done is not None:
+                node._stamp = done[1]
+                return done[0]
     prog = planner.build_program([src])
     prog.shape = tuple(child.shape)
     dev = prog.arrays[0].dev if prog.arrays else current_device()
@@ -605,7 +671,9 @@ def _run_reduce(node):
         if not axes:        # reduction over nothing: a copy
             outs, _ = evaluate_nodes([src], [result])
             return result
-        run_program(prog, [], reduce=(op, acc_dt, res_dt, post, result))
+        rec = run_program(prog, [], reduce=(op, acc_dt, res_dt, post, result))
+        if rkey is not None and rec is not None and prog.arrays:
+            _plan_record(rkey, rops, prog, [result], rec)
         return result
     lo, hi = axes[0], axes[-1] + 1
     shape = child.shape

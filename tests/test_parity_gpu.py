@@ -810,3 +810,27 @@ def test_internal_casts_never_convert_the_users_leaf(gpu):
     (f @ gpu.array(np.ones((64, 130), np.float32))).get()
     assert f.dtype == np.float64
     assert X.astype(np.float32) is X and X.dtype == np.float32          # the user-facing call IS in place
+
+
+def test_reduction_plan_cache_replays_are_exact(gpu):
+    """Prepared launches for fused full reductions (engine._reduce_plan_key): replays see the
+    current values, other layouts / dtypes / scalar classes fall back to the planner."""
+    from delayrepay_b200 import engine
+    rng = np.random.default_rng(91)
+    a, b = rng.standard_normal(100003), rng.standard_normal(100003)
+    A, B = gpu.array(a), gpu.array(b)
+    hits = engine.stats.get("plan_hits", 0)
+    for k in range(4):
+        c = float(k) + 0.5
+        np.testing.assert_allclose(float(np.sqrt(np.sum((A - B * c) ** 2))), np.sqrt(np.sum((a - b * c) ** 2)), rtol=1e-12)
+        np.testing.assert_allclose(float(np.dot(A, B)), np.dot(a, b), rtol=1e-12, atol=1e-9)
+        assert float(np.max(A)) == a.max() and float(np.min(A * c)) == (a * c).min()
+        np.testing.assert_allclose(float(np.mean(A * B)), np.mean(a * b), rtol=1e-11, atol=1e-12)
+        a[k] = 100.0 + k
+        A[k] = 100.0 + k                                  # replays must read the new data
+    assert engine.stats.get("plan_hits", 0) >= hits + 12
+    np.testing.assert_allclose(float(np.sum(A[::2])), a[::2].sum(), rtol=1e-12)          # other layout
+    np.testing.assert_allclose(float(np.sum(A[1:])), a[1:].sum(), rtol=1e-12)            # misaligned
+    a32 = a.astype(np.float32)
+    np.testing.assert_allclose(float(np.sum(gpu.array(a32))), a32.astype(np.float64).sum(), rtol=1e-6)
+    assert int(np.sum(gpu.array(np.arange(10)))) == 45 and int(np.sum(gpu.array(np.arange(12)))) == 66
