@@ -28,6 +28,10 @@ CTYPE = {
 }
 
 
+_UNSIGNED = {"b": "unsigned int", "h": "unsigned int", "i": "unsigned int", "l": "unsigned long long",
+             "q": "unsigned long long"}
+
+
 def ctype(dt):
     return CTYPE[np.dtype(dt).char]
 
@@ -100,6 +104,13 @@ def emit_expr(op, loop, out_dt, args, arg_dts, fast=False, relaxed=False, pow_mo
         return f"({a[0]} != {a[1]})"
     if op in ("true_divide", "divide") and k in "iu":       # never produced by NumPy's resolver
         raise TypeError("integer true_divide")
+    if k == "i" and op in ("add", "subtract", "multiply", "left_shift", "negative"):
+        # NumPy's signed integers wrap; in C++ signed overflow is undefined and NVRTC uses that
+        # (e.g. it widens `(double)(x * x * x)`): do the arithmetic in the unsigned type
+        U = _UNSIGNED[loop[0].char]
+        if op == "negative":
+            return f"(({O})(({U})0 - ({U}){a[0]}))"
+        return f"(({O})(({U}){a[0]} {_INFIX[op]} ({U}){a[1]}))"
     if op in _INFIX:
         e = f"({a[0]} {_INFIX[op]} {a[1]})"
         return e if out_dt.kind == "b" else f"(({O}){e})"

@@ -834,3 +834,31 @@ def test_reduction_plan_cache_replays_are_exact(gpu):
     a32 = a.astype(np.float32)
     np.testing.assert_allclose(float(np.sum(gpu.array(a32))), a32.astype(np.float64).sum(), rtol=1e-6)
     assert int(np.sum(gpu.array(np.arange(10)))) == 45 and int(np.sum(gpu.array(np.arange(12)))) == 66
+
+
+def test_signed_integer_overflow_wraps_like_numpy(gpu):
+    """Signed overflow is undefined in C++ and NVRTC uses that (it widened `(double)(x*x*x)`);
+    NumPy wraps.  Found by tools/fuzz_diff.py seed 4414."""
+    rng = np.random.default_rng(93)
+    for dt in (np.int8, np.int16, np.int32, np.int64):
+        info = np.iinfo(dt)
+        x = rng.integers(info.min, info.max, 5003, dtype=dt, endpoint=True)
+        y = rng.integers(info.min, info.max, 5003, dtype=dt, endpoint=True)
+        X, Y = gpu.array(x), gpu.array(y)
+        with np.errstate(all="ignore"):
+            cases = [(X * Y, x * y), (X + Y, x + y), (X - Y, x - y), (-X, -x), (X ** 3, (x * x) * x),
+                     (X * Y + X, x * y + x), (X << 3, x << 3),
+                     ((X * Y).astype(np.float64), (x * y).astype(np.float64))]
+            if dt in (np.int32, np.int64):       # (float functions of int8 / int16 are float16 / float32 loops)
+                cases.append((np.arcsinh((X * X) * X), np.arcsinh((x * x) * x)))
+            for got, want in cases:
+                got = got.get()
+                assert got.dtype == want.dtype
+                if want.dtype.kind == "f":
+                    np.testing.assert_allclose(got, want, rtol=1e-15)
+                else:
+                    assert np.array_equal(got, want), dt
+            if dt in (np.int32, np.int64):
+                big = rng.integers(info.max // 4, info.max, 1003, dtype=dt)
+                assert int(np.sum(gpu.array(big))) == int(np.sum(big))            # int64 accumulator wraps too
+                assert np.prod(gpu.array(big)).get() == np.prod(big)
