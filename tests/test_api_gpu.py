@@ -225,5 +225,6 @@ def test_transposed_copies_use_the_tiled_kernel_and_are_exact(gpu):
         M = gpu.array(m)
         assert np.array_equal(M[:, 17:250].T.copy().get(), m[:, 17:250].T.copy())      # pitch > width
         assert np.array_equal(M[5:, :].T.copy().get(), m[5:, :].T.copy())
-        assert np.array_equal(M[::2, :].T.copy().get(), m[::2, :].T.copy())            # not a transpose: nd path
+        assert np.array_equal(M[::2, :].T.copy().get(), m[::2, :].T.copy())            # every second row: pitch
+        assert np.array_equal(M[:, ::2].T.copy().get(), m[:, ::2].T.copy())            # strided columns: nd path
     assert any(k[0] == "transpose" for k in engine._kernels), "tiled transpose not taken"

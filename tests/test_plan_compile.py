@@ -202,3 +202,84 @@ def test_no_cpu_fallback_without_device():
     x = dr.array(np.ones(8))               # host-backed leaf: graph building only
     with pytest.raises(_lib.DrcError):
         (x + 1).get()
+
+
+# ------------------------------------------------------------------ host logic of this round's kernels
+def test_axis_reduction_dispatch_vectors_splits_and_transposed_views():
+    """rows / cols selection, 128-bit operand classes, the split reduced axis (two launches, the
+    second folds the partials) and the transposed dispatch, observed through dry-run launches."""
+    import delayrepay_b200 as dr
+    from delayrepay_b200 import engine
+
+    def families(fn):
+        n0 = len(engine.dry_log)
+        fn().run()
+        return [k[0].name.split("_")[1] for k in engine.dry_log[n0:]], engine.dry_log[n0:]
+
+    with engine.dry_run():
+        X = dr.array(np.ones((2048, 512), np.float32))
+        v0, v1 = dr.array(np.ones(2048, np.float32)), dr.array(np.ones(512, np.float32))
+        fam, launches = families(lambda: np.sum(X, axis=0))
+        assert len(fam) >= 2 and set(fam) == {"cols"} and launches[0][1][1] > 1, \
+            "tall matrix: reduced axis split over grid.y, partials folded by the same family"
+        assert "dr_ld<false, float, 4>" in launches[0][0].source, "contiguous operand read with 128-bit loads"
+        assert families(lambda: np.sum(X, axis=1))[0] == ["rows"]
+        assert families(lambda: X @ v1)[0] == ["rows"]
+        assert set(families(lambda: v0 @ X)[0]) == {"cols"}, "v @ X walks X's rows contiguously"
+        assert set(families(lambda: np.sum(X.T, axis=1))[0]) == {"cols"}, "transposed view: column kernel"
+        fam, launches = families(lambda: np.sum(X[:, 1:], axis=0))
+        assert "dr_ld<false, float, 4>" not in launches[0][0].source, "misaligned rows: scalar loads"
+        wide = dr.array(np.ones((4, 1 << 16), np.float64))
+        assert families(lambda: np.max(wide, axis=0))[0] == ["cols"], "enough columns: no split"
+
+
+def test_internal_promotions_leave_the_leaf_alone_and_integers_wrap():
+    import delayrepay_b200 as dr
+    from delayrepay_b200 import engine
+    with engine.dry_run():
+        x = dr.array(np.arange(12, dtype=np.int32).reshape(3, 4))
+        for use in (lambda: np.sum(x), lambda: np.mean(x, axis=0), lambda: np.sum(x, dtype=np.float32),
+                    lambda: x @ dr.array(np.ones(4)), lambda: np.cumsum(x, dtype=np.float64)):
+            use().run()
+            assert x.dtype == np.int32 and x._force().dtype == np.int32
+        n0 = len(engine.dry_log)
+        ((x * x) * x - x).run()
+        src = engine.dry_log[n0][0].source
+        assert "(unsigned int)x0 * (unsigned int)x0" in src, "signed arithmetic must be emitted unsigned (wraps)"
+        assert x.astype(np.float32) is x and x.dtype == np.float32        # the user-facing astype is in place
+
+
+def test_transposed_source_detection():
+    from delayrepay_b200 import engine, extras
+    import delayrepay_b200 as dr
+    with engine.dry_run():
+        a = dr.array(np.ones((64, 96), np.float32))._force()
+        assert extras.transposed_source(a.T) == (1, 64, 96)
+        assert extras.transposed_source(a) is None
+        assert extras.transposed_source(a[:, 8:72].T) == (1, 64, 64), "column block: pitch > width"
+        assert extras.transposed_source(a[::2].T) == (1, 32, 96), "every second row: a larger pitch"
+        assert extras.transposed_source(a[:, ::2].T) is None, "strided columns are not a transpose"
+        b = dr.array(np.ones((3, 40, 50), np.float64))._force()
+        assert extras.transposed_source(b.transpose(0, 2, 1)) == (3, 40, 50)
+        assert extras.transposed_source(dr.array(np.ones((8, 8), np.float32))._force().T) is None, "too small"
+        assert extras.transposed_source(dr.array(np.ones((64, 64), np.int8))._force().T) is None, "1-byte words"
+
+
+def test_numpy_surface_registry_and_module_passthrough():
+    import delayrepay as dnp
+    from delayrepay_b200 import HANDLED_FUNCTIONS
+    for fn in (np.sum, np.prod, np.max, np.min, np.mean, np.var, np.std, np.average, np.linalg.norm, np.where,
+               np.clip, np.any, np.all, np.count_nonzero, np.argmax, np.argmin, np.ptp, np.trace, np.cumsum,
+               np.transpose, np.roll, np.repeat, np.tile, np.diag, np.diagflat, np.reshape, np.ravel, np.squeeze,
+               np.expand_dims, np.swapaxes, np.moveaxis, np.broadcast_to, np.concatenate, np.stack, np.vstack,
+               np.hstack, np.outer, np.inner, np.vdot, np.diff, np.round, np.around, np.isclose, np.allclose,
+               np.array_equal, np.take, np.compress, np.extract, np.nonzero, np.flatnonzero, np.argwhere,
+               np.zeros_like, np.ones_like, np.empty_like, np.full_like, np.shape, np.size, np.ndim, np.copy,
+               np.matmul):
+        assert fn in HANDLED_FUNCTIONS, fn.__name__
+    assert dnp.floor is np.floor and dnp.inf == np.inf and dnp.int8 is np.int8 and dnp.linalg is np.linalg
+    with pytest.raises(AttributeError):
+        dnp.definitely_not_a_numpy_name
+    x = dnp.array(np.ones(4))
+    with pytest.raises(KeyError):               # no device implementation: loud, never a host fallback
+        np.sort(x)
