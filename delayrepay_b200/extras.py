@@ -615,7 +615,9 @@ def compress(src, mask):
     rows, inner = _mask_layout(src, mask)
     if inner == 1 and rows > 0:
         mask, offsets, count, ntiles, ks = _mask_tiles(mask, _word_size(src.dtype))
-        out = DeviceArray.empty((count,), src.dtype, src.dev if src.dev >= 0 else None)
+        # (trailing dimensions of size 1 stay: a row mask on an (n, 1) array gives (count, 1))
+        out = DeviceArray.empty((count,) + tuple(src.shape[mask.ndim:]), src.dtype,
+                                src.dev if src.dev >= 0 else None)
         if count or src.dev < 0:
             _mask_scatter(ks, src, mask, offsets, out, rows, ntiles, 0)
         return out

@@ -202,6 +202,14 @@ def test_integer_array_and_boolean_mask_indexing(gpu):
         h2[rm] = fill
         d2[gpu.array(rm)] = fill
         assert np.array_equal(d2.get(), h2)
+    col = np.arange(7.0).reshape(7, 1)                  # trailing unit dimensions survive a row mask
+    keep = np.array([True, False, True, True, False, False, True])
+    got = gpu.array(col)[gpu.array(keep)].get()
+    assert got.shape == (4, 1) and np.array_equal(got, col[keep])
+    assert np.array_equal(np.compress(keep[:2], gpu.array(np.ones((1, 2))), axis=1).get(),
+                          np.compress(keep[:2], np.ones((1, 2)), axis=1))
+    assert np.array_equal(np.compress(keep, gpu.array(col.reshape(1, 7, 1)), axis=-2).get(),
+                          np.compress(keep, col.reshape(1, 7, 1), axis=-2))
     with pytest.raises(IndexError):
         gpu.array(np.arange(5.0))[gpu.array(np.array([1, 5]))]
     with pytest.raises(IndexError):

@@ -283,3 +283,15 @@ def test_numpy_surface_registry_and_module_passthrough():
     x = dnp.array(np.ones(4))
     with pytest.raises(KeyError):               # no device implementation: loud, never a host fallback
         np.sort(x)
+
+
+def test_numpy_surface_shapes_and_dtypes_match_numpy_without_a_device():
+    """tools/fuzz_shapes.py: every handler of the NumPy surface with random shapes, dtypes, axes
+    and keywords, planned and compiled in dry-run mode; result shapes and dtypes must be NumPy's
+    (values are the GPU tests' job).  Found: a row mask on an (n, 1) array dropped the unit axis."""
+    import subprocess
+    import sys
+    tool = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "fuzz_shapes.py")
+    out = subprocess.run([sys.executable, tool, "--n", "150"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert out.stdout.strip().splitlines()[-1].startswith("fuzz_shapes: 0 failing"), out.stdout[-3000:]
