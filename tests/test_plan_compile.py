@@ -1,5 +1,7 @@
 """Host logic without a GPU: capture, hash-consing, planning, code generation and NVRTC
 compilation of every workload (engine.dry_run: placeholder addresses, launches recorded)."""
+import os
+
 import numpy as np
 import pytest
 
