@@ -1024,15 +1024,41 @@ def implements(np_function):
     return decorator
 
 
-def _reduce(ufunc, arr, axis=None, dtype=None, out=None, keepdims=False, post=None, **kw):
+def _no_extra(fn, kw):
+    """Keyword arguments a handler does not implement must never be ignored silently."""
+    extra = {k: v for k, v in kw.items() if v is not np._NoValue and v is not None}
+    if extra:
+        raise NotImplementedError(f"{fn}: unsupported keyword argument(s) {sorted(extra)}")
+
+
+def _reduce(ufunc, arr, axis=None, dtype=None, out=None, keepdims=False, post=None,
+            initial=np._NoValue, where=np._NoValue, **kw):
     if out is not None:
         raise NotImplementedError("out= is not supported")
+    _no_extra(ufunc.__name__ + ".reduce", kw)
     node = arg_to_numpy_ex(arr)
     if dtype is not None:
         node = as_dtype(node, dtype)
     if keepdims is np._NoValue:
         keepdims = False
-    return ReduceEx(ufunc, node, _norm_axis(axis), bool(keepdims), post)
+    if where is not np._NoValue and where is not True:
+        # masked reduction: unselected elements contribute the identity (fused select)
+        if post is not None:
+            raise NotImplementedError("where= is not supported for mean")
+        ident = {"add": 0, "multiply": 1}.get(ufunc.__name__)
+        if ident is None:
+            if initial is np._NoValue:
+                raise ValueError(f"reduction operation '{ufunc.__name__}' does not have an identity, so to "
+                                 "use a where mask one has to specify 'initial'")
+            ident = initial
+        node = WhereEx(arg_to_numpy_ex(where), node, arg_to_numpy_ex(ident))
+    res = ReduceEx(ufunc, node, _norm_axis(axis), bool(keepdims), post)
+    if initial is not np._NoValue and initial is not None:
+        if post is not None:
+            raise NotImplementedError("initial= is not supported for mean")
+        # NumPy casts `initial` to the reduction's dtype (np.max(int32_array, initial=2.5) is int32)
+        res = create_ex(ufunc, [res, Scalar(res.dtype.type(initial))])
+    return res
 
 
 @implements(np.sum)
@@ -1064,12 +1090,21 @@ def mean(arr, *args, **kwargs):
 def average(arr, axis=None, weights=None, **kwargs):            # [delayarray.py:544-546]
     if weights is None:
         return mean(arr, axis=axis, **kwargs)
-    w = arg_to_numpy_ex(weights)
-    return np.sum(arg_to_numpy_ex(arr) * w, axis=axis) / np.sum(w, axis=axis)
+    _no_extra("average", {k: v for k, v in kwargs.items() if k != "keepdims"})
+    x = arg_to_numpy_ex(arr)
+    w = arg_to_numpy_ex(np.asarray(weights) if isinstance(weights, (list, tuple)) else weights)
+    if w.ndim == 1 and x.ndim > 1 and axis is not None:      # 1-d weights run along `axis`
+        w = w.reshape(tuple(-1 if i == axis % x.ndim else 1 for i in range(x.ndim)))
+    keep = bool(kwargs.get("keepdims", False)) if kwargs.get("keepdims", False) is not np._NoValue else False
+    return np.sum(x * w, axis=axis, keepdims=keep) / np.sum(np.broadcast_to(w, x.shape) if w.shape != x.shape else w,
+                                                            axis=axis, keepdims=keep)
 
 
 @implements(np.var)
 def var(arr, axis=None, dtype=None, out=None, ddof=0, keepdims=False, **kw):   # [:511-513]
+    _no_extra("var", dict(kw, out=out))
+    if keepdims is np._NoValue:
+        keepdims = False
     x = arg_to_numpy_ex(arr)
     if dtype is not None:
         x = as_dtype(x, dtype)
@@ -1104,6 +1139,9 @@ def where(cond, a=None, b=None):
 
 @implements(np.clip)
 def clip(a, a_min=None, a_max=None, **kw):
+    a_min = kw.pop("min", a_min) if a_min is None else a_min          # NumPy >= 2.1 spellings
+    a_max = kw.pop("max", a_max) if a_max is None else a_max
+    _no_extra("clip", kw)
     res = arg_to_numpy_ex(a)
     if a_min is not None:
         res = np.maximum(res, a_min)
@@ -1125,6 +1163,19 @@ def matmul(a, b, **kw):
 
 @implements(np.roll)
 def roll(arr, shift, axis=None):                                 # [delayarray.py:527-530]
+    if isinstance(axis, (tuple, list)):                          # several axes: one roll per axis
+        shifts = shift if isinstance(shift, (tuple, list)) else (shift,) * len(axis)
+        if len(shifts) != len(axis):
+            raise ValueError("'shift' and 'axis' should be scalars or 1D sequences of the same length")
+        res = arr
+        for sh, ax_ in zip(shifts, axis):
+            res = roll(res, sh, ax_)
+        return res
+    if isinstance(shift, (tuple, list)):
+        res = arr
+        for sh in shift:
+            res = roll(res, sh, axis)
+        return res
     src = arg_to_numpy_ex(arr)._force()
     flat = src.reshape(-1) if axis is None else src
     ax = 0 if axis is None else axis % flat.ndim
@@ -1315,11 +1366,13 @@ def _store_out(res, out):
 
 @implements(np.any)
 def any(arr, axis=None, out=None, keepdims=False, **kw):          # noqa: A001
+    _no_extra("any", kw)
     return _reduce(np.maximum, np.not_equal(arg_to_numpy_ex(arr), 0), axis, None, out, keepdims)
 
 
 @implements(np.all)
 def all(arr, axis=None, out=None, keepdims=False, **kw):          # noqa: A001
+    _no_extra("all", kw)
     return _reduce(np.minimum, np.not_equal(arg_to_numpy_ex(arr), 0), axis, None, out, keepdims)
 
 
