@@ -252,13 +252,17 @@ class DelayArray(numpy.lib.mixins.NDArrayOperatorsMixin):
         return self._dot([other, self])
 
     def dot(self, other, out=None):
+        if out is not None:
+            raise NotImplementedError("dot: out= is not supported")
         # the reference passes `other` as the argument list and returns b[0].b[1]
         # (delayarray.py:98-99); NumPy semantics are implemented instead.
         return self._dot([self, other])
 
     # ---- views and assignment  [delayarray.py:111-128]
     def reshape(self, *args, **kwargs):
-        return NPArray(self._force().reshape(*args, **kwargs))
+        if kwargs.pop("order", "C") not in ("C", None) or kwargs:
+            raise NotImplementedError("reshape: only C order is supported")
+        return NPArray(self._force().reshape(*args))
 
     def __getitem__(self, key):
         ia = _index_array(key)
@@ -1158,6 +1162,7 @@ def transpose(arr, axes=None):                                   # [delayarray.p
 
 @implements(np.matmul)
 def matmul(a, b, **kw):
+    _no_extra("matmul", kw)
     return arg_to_numpy_ex(a)._dot([a, b]) if isinstance(a, DelayArray) else b._dot([a, b])
 
 
@@ -1255,6 +1260,7 @@ def diagflat(arr, k=0):                                          # [delayarray.p
 @implements(np.cumsum)
 def cumsum(arr, axis=None, dtype=None, out=None):                # [delayarray.py:555-558]
     from . import engine
+    _no_extra("cumsum", {"out": out})
     node = arg_to_numpy_ex(arr)
     if dtype is not None:
         node = as_dtype(node, dtype)
@@ -1287,6 +1293,7 @@ def _index_array(key):
 
 @implements(np.take)
 def take(arr, indices, axis=None, out=None, mode="raise"):
+    _no_extra("take", {"out": out, "mode": None if mode == "raise" else mode})
     x = arg_to_numpy_ex(arr)
     if axis is None:
         x = x.reshape(-1)
@@ -1297,6 +1304,7 @@ def take(arr, indices, axis=None, out=None, mode="raise"):
 
 @implements(np.compress)
 def compress(condition, arr, axis=None, out=None):
+    _no_extra("compress", {"out": out})
     x = arg_to_numpy_ex(arr)
     cond = arg_to_numpy_ex(np.asarray(condition) if isinstance(condition, (list, tuple)) else condition)
     cond = cond if cond.dtype == np.dtype(bool) else np.not_equal(cond, 0)
@@ -1394,22 +1402,28 @@ def _arg_extreme(arr, axis, keepdims, is_max):
 
 @implements(np.argmax)
 def argmax(arr, axis=None, out=None, keepdims=False):
+    _no_extra("argmax", {"out": out})
     return _arg_extreme(arr, axis, keepdims, True)
 
 
 @implements(np.argmin)
 def argmin(arr, axis=None, out=None, keepdims=False):
+    _no_extra("argmin", {"out": out})
     return _arg_extreme(arr, axis, keepdims, False)
 
 
 @implements(np.ptp)
 def ptp(arr, axis=None, out=None, keepdims=False):
+    _no_extra("ptp", {"out": out})
     x = arg_to_numpy_ex(arr)
     return np.max(x, axis=axis, keepdims=keepdims) - np.min(x, axis=axis, keepdims=keepdims)
 
 
 @implements(np.trace)
 def trace(arr, offset=0, **kw):
+    _no_extra("trace", {k: v for k, v in kw.items() if not (k in ("axis1", "axis2") and v == {"axis1": 0, "axis2": 1}[k])})
+    if arg_to_numpy_ex(arr).ndim != 2:
+        raise NotImplementedError("np.trace is supported for matrices only")
     return np.sum(diag(arr, offset))
 
 
@@ -1420,12 +1434,15 @@ def _dev(a):
 
 @implements(np.reshape)
 def reshape(arr, *args, **kwargs):
+    _no_extra("reshape", {"order": None if kwargs.pop("order", "C") in ("C", None) else "non-C",
+                          "copy": kwargs.pop("copy", None)})
     shape = kwargs.pop("shape", None) or kwargs.pop("newshape", None) or args[0]
     return arg_to_numpy_ex(arr).reshape(shape)
 
 
 @implements(np.ravel)
 def ravel(arr, order="C"):
+    _no_extra("ravel", {"order": None if order == "C" else order})
     return arg_to_numpy_ex(arr).reshape(-1)
 
 
@@ -1514,18 +1531,21 @@ def stack(arrays, axis=0, out=None, **kw):
 
 @implements(np.vstack)
 def vstack(tup, **kw):
+    _no_extra("vstack", kw)
     parts = [arg_to_numpy_ex(a) for a in tup]
     return concatenate([p_.reshape(1, -1) if p_.ndim < 2 else p_ for p_ in parts], axis=0)
 
 
 @implements(np.hstack)
 def hstack(tup, **kw):
+    _no_extra("hstack", kw)
     parts = [arg_to_numpy_ex(a) for a in tup]
     return concatenate(parts, axis=0 if parts[0].ndim == 1 else 1)
 
 
 @implements(np.outer)
 def outer(a, b, out=None):
+    _no_extra("outer", {"out": out})
     return arg_to_numpy_ex(a).reshape(-1, 1) * arg_to_numpy_ex(b).reshape(1, -1)
 
 
@@ -1557,6 +1577,7 @@ def diff(arr, n=1, axis=-1, **kw):
 
 @implements(np.round)
 def round(arr, decimals=0, out=None):                             # noqa: A001
+    _no_extra("round", {"out": out})
     x = arg_to_numpy_ex(arr)
     if x.dtype.kind != "f":
         if decimals >= 0:
