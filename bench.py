@@ -78,7 +78,7 @@ class ClockSampler(threading.Thread):
 def cpu_black_scholes(log2n, reps=1):
     """The reference's CPU path (oracle port, oracle/refcpu.py) on a bounded sample."""
     from oracle import refcpu
-    from delayrepay_b200 import workloads as wl
+    import workloads as wl
     n = 1 << log2n
     inp = wl.make_inputs("black_scholes", n)
     best = float("inf")
@@ -216,7 +216,8 @@ def main():
     import torch
     import torch.distributed as dist
     import delayrepay_b200 as dr
-    from delayrepay_b200 import engine, workloads as wl
+    from delayrepay_b200 import engine
+    import workloads as wl
     from delayrepay_b200._lib import lib, check
     import ctypes as C
 

@@ -85,10 +85,18 @@ class Memoiser(type):
         if key is None:
             return super().__call__(*args, **kwargs)
         hit = Memoiser._cache.get(key)
-        if hit is not None and hit.__dict__.get("array") is not None and not _stamp_valid(hit._stamp):
-            # evaluated before one of its inputs was written: that node keeps ITS value (whoever
-            # holds it sees a snapshot, as with NumPy); this new capture must see the new data
-            hit = None
+        if hit is not None and hit.kind == "leaf":
+            if "_dev" in hit.__dict__:       # host leaf already uploaded: see NPArray._memo_key
+                hit = None
+        elif hit is not None:
+            arr = hit.__dict__.get("array")
+            if arr is not None and (not _stamp_valid(hit._stamp) or arr.buf.version != 0):
+                # evaluated before one of its inputs was written: that node keeps ITS value
+                # (whoever holds it sees a snapshot, as with NumPy); this new capture must see the
+                # new data.  Likewise a node whose OWN result storage was written afterwards
+                # (`c = a*2; c[1:3] = 0`): results live in fresh buffers (version 0) and every
+                # in-place write bumps the version, so a fresh capture of `a*2` recomputes.
+                hit = None
         if hit is None:
             hit = super().__call__(*args, **kwargs)
             Memoiser._cache[key] = hit
@@ -181,7 +189,7 @@ class DelayArray(numpy.lib.mixins.NDArrayOperatorsMixin):
     # ---- capture  [delayarray.py:46-61]
     def __array_ufunc__(self, ufunc, method, *inputs, **kwargs):
         out = kwargs.pop("out", None)
-        if kwargs.pop("where", True) is not True:
+        if method != "reduce" and kwargs.pop("where", True) is not True:
             return NotImplemented
         dtype = kwargs.pop("dtype", None)
         name = ufunc.__name__
@@ -190,9 +198,11 @@ class DelayArray(numpy.lib.mixins.NDArrayOperatorsMixin):
         if method == "reduce":
             if name not in _REDUCE_UFUNCS:
                 raise KeyError(name)
-            res = ReduceEx(ufunc, arg_to_numpy_ex(inputs[0]), _norm_axis(kwargs.get("axis", 0)),
-                           bool(kwargs.get("keepdims", False)))
-            return res if dtype is None else as_dtype(res, dtype)
+            # same path as np.sum / np.max ...: initial= and where= are honoured, anything
+            # else raises (never ignored)
+            if "where" in kwargs and kwargs["where"] is True:
+                kwargs.pop("where")
+            return _reduce(ufunc, inputs[0], kwargs.pop("axis", 0), dtype, out, **kwargs)
         if method != "__call__":
             return NotImplemented
         if name == "matmul":
@@ -366,7 +376,13 @@ class DelayArray(numpy.lib.mixins.NDArrayOperatorsMixin):
         self._force().fill(value)
 
     def conj(self):
-        return self
+        if self.dtype.kind != "c":
+            return self
+        src = self._force()
+        out = DeviceArray.empty(src.shape, src.dtype, src.dev)
+        _complex_part(out, 0)[...] = NPArray(_complex_part(src, 0))
+        _complex_part(out, 1)[...] = -NPArray(_complex_part(src, 1))
+        return NPArray(out)
 
     conjugate = conj
 
@@ -381,10 +397,14 @@ class DelayArray(numpy.lib.mixins.NDArrayOperatorsMixin):
 
     @property
     def real(self):
+        if self.dtype.kind == "c":          # fft results: strided view of the interleaved pairs
+            return NPArray(_complex_part(self._force(), 0))
         return self
 
     @property
     def imag(self):
+        if self.dtype.kind == "c":
+            return NPArray(_complex_part(self._force(), 1))
         return zeros_like(self)
 
     @property
@@ -432,6 +452,12 @@ class DelayArray(numpy.lib.mixins.NDArrayOperatorsMixin):
         return dict(sorted(found.items(), key=lambda kv: kv[1]._count))
 
 
+def _complex_part(arr, which):
+    """Float view (0 = real, 1 = imaginary) over the interleaved storage of a complex array."""
+    part = np.dtype(np.float32 if arr.dtype == np.complex64 else np.float64)
+    return DeviceArray(arr.buf, arr.shape, part, arr.strides, arr.offset + which * part.itemsize)
+
+
 def _stamp_valid(stamp):
     if stamp is None:
         return True
@@ -446,6 +472,12 @@ def _norm_axis(axis):
     if axis is None or isinstance(axis, tuple):
         return axis
     return int(axis)
+
+
+def _normalize_axes(axis, ndim):
+    """NumPy's own validation: AxisError for out-of-range axes, ValueError for duplicates."""
+    from numpy.lib.array_utils import normalize_axis_tuple
+    return normalize_axis_tuple(axis, ndim)
 
 
 Shape = tuple
@@ -739,10 +771,12 @@ class ReduceEx(NumpyEx, Funcable):
         if axis is None:
             axes = tuple(range(nd))
         else:
-            axes = tuple(sorted({(a + nd) % nd if nd else 0 for a in
-                                 (axis if isinstance(axis, tuple) else (axis,))}))
             if nd == 0:
+                # NumPy accepts axis 0 / -1 / () on a 0-d operand and nothing else
+                _normalize_axes(axis, 1)
                 axes = ()
+            else:
+                axes = tuple(sorted(_normalize_axes(axis, nd)))
         self.axes = axes
         self.keepdims = keepdims
         self.shape = tuple((1 if i in axes else s) for i, s in enumerate(arg.shape)
@@ -849,7 +883,11 @@ class NPArray(NumpyEx):
         if isinstance(array, DeviceArray):
             return ("NPArray",) + array.layout_key()      # the same slice twice is one leaf
         if isinstance(array, np.ndarray):
-            return ("NPArray", id(array))                  # reference: id(array), :225-226
+            # reference: id(array), :225-226 (tests/test.py:145-149 wants NPArray(a) is NPArray(a)).
+            # Memoiser.__call__ stops returning this leaf once it has been uploaded: a host array
+            # can be written in place behind our back, so a capture made after an evaluation
+            # uploads the data as it is then
+            return ("NPArray", id(array))
         return None
 
     def _force(self):
@@ -873,9 +911,11 @@ class NPArray(NumpyEx):
         self.array = self.array.astype(dtype)
         self.__dict__.pop("_dev", None)
         self.dtype = self.array.dtype
-        if Memoiser._cache.get(old_key) is self:
+        if old_key is not None and Memoiser._cache.get(old_key) is self:
             del Memoiser._cache[old_key]
-        Memoiser._cache[self._memo_key(self.array)] = self
+        new_key = self._memo_key(self.array)
+        if new_key is not None:
+            Memoiser._cache[new_key] = self
         return self
 
     @property
@@ -965,8 +1005,7 @@ def arg_to_numpy_ex(arg):
         return NPArray(arg)
     if isinstance(arg, (list, tuple)):
         return NPArray(np.asarray(arg))
-    print(type(arg))
-    raise NotImplementedError
+    raise NotImplementedError(f"cannot capture an operand of type {type(arg).__name__}")
 
 
 def pow_ex(func, left, right):
@@ -1097,8 +1136,15 @@ def average(arr, axis=None, weights=None, **kwargs):            # [delayarray.py
     _no_extra("average", {k: v for k, v in kwargs.items() if k != "keepdims"})
     x = arg_to_numpy_ex(arr)
     w = arg_to_numpy_ex(np.asarray(weights) if isinstance(weights, (list, tuple)) else weights)
-    if w.ndim == 1 and x.ndim > 1 and axis is not None:      # 1-d weights run along `axis`
-        w = w.reshape(tuple(-1 if i == axis % x.ndim else 1 for i in range(x.ndim)))
+    if tuple(w.shape) != tuple(x.shape):
+        if axis is None:
+            raise TypeError("Axis must be specified when shapes of a and weights differ.")
+        ax = _normalize_axes(axis, x.ndim)
+        if w.ndim != 1 or len(ax) != 1:
+            raise TypeError("1D weights expected when shapes of a and weights differ.")
+        if w.shape[0] != x.shape[ax[0]]:
+            raise ValueError("Length of weights not compatible with specified axis.")
+        w = w.reshape(tuple(-1 if i == ax[0] else 1 for i in range(x.ndim)))   # along `axis`
     keep = bool(kwargs.get("keepdims", False)) if kwargs.get("keepdims", False) is not np._NoValue else False
     return np.sum(x * w, axis=axis, keepdims=keep) / np.sum(np.broadcast_to(w, x.shape) if w.shape != x.shape else w,
                                                             axis=axis, keepdims=keep)
@@ -1296,10 +1342,19 @@ def take(arr, indices, axis=None, out=None, mode="raise"):
     _no_extra("take", {"out": out, "mode": None if mode == "raise" else mode})
     x = arg_to_numpy_ex(arr)
     if axis is None:
-        x = x.reshape(-1)
-    elif axis % x.ndim != 0:
-        return swapaxes(swapaxes(x, 0, axis)[indices], 0, axis)
-    return x[indices if not np.isscalar(indices) else int(indices)]
+        x, axis = x.reshape(-1), 0
+    axis = _normalize_axes(axis, x.ndim)[0]
+    idx = indices if isinstance(indices, (DelayArray, DeviceArray)) else np.asarray(indices)
+    if idx.dtype.kind not in "iu":
+        raise TypeError("Cannot cast array data from indices to an integer type")
+    if axis == 0:
+        return x[int(idx) if idx.ndim == 0 else idx]
+    # gather along the leading axis, then move the idx.ndim new leading axes back to `axis`
+    # (none for a scalar index): result shape = x.shape[:axis] + idx.shape + x.shape[axis+1:]
+    got = moveaxis(x, axis, 0)[int(idx) if idx.ndim == 0 else idx]
+    if idx.ndim == 0:
+        return got
+    return moveaxis(got, tuple(range(idx.ndim)), tuple(range(axis, axis + idx.ndim)))
 
 
 @implements(np.compress)

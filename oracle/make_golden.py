@@ -30,7 +30,7 @@ with contextlib.redirect_stdout(io.StringIO()):       # backend.py:4 prints on i
 
 assert ref.__file__.startswith("/root/reference"), ref.__file__
 
-from delayrepay_b200 import workloads as wl          # noqa: E402
+import workloads as wl          # noqa: E402
 from oracle import refcpu                            # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")

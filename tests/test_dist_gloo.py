@@ -24,7 +24,8 @@ def _free_port():
 def _worker(rank, world, port, out):
     sys.path.insert(0, ROOT)
     import torch.distributed as dist
-    from delayrepay_b200 import dist as dd, workloads as wl
+    from delayrepay_b200 import dist as dd
+    import workloads as wl
     from oracle import refcpu
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     comm = dd.GlooComm()
@@ -74,7 +75,7 @@ def test_shard_bounds_cover_the_axis():
 @pytest.mark.timeout(180)
 def test_sharded_reductions_and_heat_world2():
     import torch.multiprocessing as mp
-    from delayrepay_b200 import workloads as wl
+    import workloads as wl
     from oracle import refcpu
     world, port = 2, _free_port()
     mgr = mp.Manager()

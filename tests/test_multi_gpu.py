@@ -22,7 +22,8 @@ def _worker(rank, world, port, out):
     sys.path.insert(0, ROOT)
     import torch.distributed as tdist
     import delayrepay_b200 as dr
-    from delayrepay_b200 import dist as dd, workloads as wl
+    from delayrepay_b200 import dist as dd
+    import workloads as wl
     tdist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     dr.set_device(rank)
     comm = dd.NcclComm(rank, world, rank)
@@ -53,7 +54,7 @@ def test_two_gpu_sharded_reductions_and_heat(gpu):
     if init() < 2:
         pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
     import torch.multiprocessing as mp
-    from delayrepay_b200 import workloads as wl
+    import workloads as wl
     from oracle import refcpu
     world, port = 2, _free_port()
     out = mp.Manager().dict()

@@ -5,7 +5,7 @@ import os
 import numpy as np
 import pytest
 
-from delayrepay_b200 import workloads as wl
+import workloads as wl
 from oracle import refcpu
 from util import assert_bits_equal
 

@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 from scipy.special import erf
 
-from delayrepay_b200 import workloads as wl
+import workloads as wl
 from oracle import refcpu
 from util import (assert_bits_equal, assert_close_to_numpy_or_truth, assert_ulp, erf_exact,
                   ulp_distance)

@@ -6,7 +6,8 @@ import numpy as np
 import pytest
 
 import delayrepay_b200 as dr
-from delayrepay_b200 import engine, planner, workloads as wl
+from delayrepay_b200 import engine, planner
+import workloads as wl
 
 
 @pytest.fixture()

@@ -1,0 +1,89 @@
+"""Round-2 regressions: stale memo hits after host / self writes, np.take
+along a non-zero axis, axis validation, ufunc.reduce keywords, np.average argument checks and
+complex parts of fft results.  Shapes are checked in dry-run mode on the CPU; values on the GPU."""
+import numpy as np
+import pytest
+
+import delayrepay_b200 as dr
+from delayrepay_b200 import engine
+
+
+def test_take_shapes_match_numpy():
+    x = np.zeros((3, 4, 5), np.float32)
+    cases = [(2, 1), (np.array([[0, 1], [2, 3]]), 1), ([1, 2], 2), (1, -1), ([0, 2], 0), (3, None)]
+    with engine.dry_run():
+        d = dr.array(x)
+        for idx, ax in cases:
+            assert np.take(d, idx, axis=ax).shape == np.take(x, idx, axis=ax).shape, (idx, ax)
+        y = dr.array(np.zeros((3, 4)))
+        assert np.take(y, 1, axis=1).shape == (3,)
+
+
+def test_axes_are_validated_like_numpy():
+    with engine.dry_run():
+        y = dr.array(np.zeros((3, 4)))
+        for bad in (5, -3, 2):
+            with pytest.raises(np.exceptions.AxisError):
+                np.sum(y, axis=bad)
+        with pytest.raises(ValueError):
+            np.sum(y, axis=(0, 0))
+        with pytest.raises(TypeError):
+            np.average(y, weights=np.ones(4))            # shapes differ, no axis
+        with pytest.raises(ValueError):
+            np.average(y, weights=np.ones(3), axis=1)    # wrong length
+        assert np.average(y, weights=np.ones(4), axis=1).shape == (3,)
+        assert np.add.reduce(y, initial=5).shape == (4,)
+        assert np.add.reduce(y, axis=1, keepdims=True).shape == (3, 1)
+
+
+def test_memo_is_not_hit_after_self_write_or_for_host_operands():
+    with engine.dry_run():
+        a = dr.array(np.arange(8.0))
+        c = a * 2
+        c._force()
+        c[1:3] = 0
+        assert (a * 2) is not c                 # c was written in place: a fresh capture recomputes
+        assert np.sin(a) is np.sin(a)           # hash-consing of untouched nodes is kept
+        h = np.ones(8)
+        r = a + h
+        assert (a + h) is r                     # reference tests/test.py:145-149: host leaves memoise
+        r._force()                              # ... until they have been uploaded
+        assert (a + h) is not r
+
+
+@pytest.mark.gpu
+def test_advice_values(gpu):
+    rng = np.random.default_rng(7)
+    x = rng.standard_normal((3, 4, 5)).astype(np.float32)
+    d = dr.array(x)
+    for idx, ax in [(2, 1), (np.array([[0, 1], [2, 3]]), 1), ([1, 2], 2), ([0, 2], 0), (7, None)]:
+        np.testing.assert_array_equal(np.take(d, idx, axis=ax).get(), np.take(x, idx, axis=ax))
+    # self-write invalidates the memoised node, holders of the old node keep its (mutated) storage
+    a = dr.array(np.arange(8.0))
+    c = a * 2
+    c._force()
+    c[1:3] = 0
+    np.testing.assert_array_equal((a * 2).get(), np.arange(8.0) * 2)
+    np.testing.assert_array_equal(c.get(), np.where((np.arange(8) >= 1) & (np.arange(8) < 3), 0, np.arange(8.0) * 2))
+    # host operand mutated between captures
+    h = np.ones(8)
+    r = a + h
+    r._force()
+    h[:] = 7
+    np.testing.assert_array_equal((a + h).get(), np.arange(8.0) + 7)
+    y = rng.standard_normal((3, 4))
+    dy = dr.array(y)
+    np.testing.assert_allclose(np.add.reduce(dy, initial=5).get(), np.add.reduce(y, initial=5), rtol=1e-12)
+    np.testing.assert_allclose(np.average(dy, weights=np.arange(1.0, 5.0), axis=1).get(),
+                               np.average(y, weights=np.arange(1.0, 5.0), axis=1), rtol=1e-12)
+
+
+@pytest.mark.gpu
+def test_complex_parts_of_fft_results(gpu):
+    rng = np.random.default_rng(8)
+    x = rng.standard_normal(256)
+    f = dr.fft.fft(dr.array(x))
+    want = np.fft.fft(x)
+    np.testing.assert_allclose(f.real.get(), want.real, atol=1e-9)
+    np.testing.assert_allclose(f.imag.get(), want.imag, atol=1e-9)
+    np.testing.assert_allclose(f.conj().get(), want.conj(), atol=1e-9)

@@ -15,7 +15,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 
 import delayrepay_b200 as dr
-from delayrepay_b200 import workloads as wl
+import workloads as wl
 from delayrepay_b200._lib import check, lib
 from delayrepay_b200.device import DeviceArray
 from delayrepay_b200.stream import H2D, D2H

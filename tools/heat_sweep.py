@@ -2,7 +2,7 @@
 import ctypes as C, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import delayrepay_b200 as dr
-from delayrepay_b200 import workloads as wl
+import workloads as wl
 from delayrepay_b200._lib import lib, check
 dr.set_device(0)
 g = 32768

@@ -8,7 +8,8 @@ import time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import delayrepay_b200 as dr
-from delayrepay_b200 import planner, engine, workloads as wl
+from delayrepay_b200 import planner, engine
+import workloads as wl
 
 dr.set_device(0)
 n = 1 << 24

@@ -15,7 +15,8 @@ import numpy as np
 import torch
 import torch.distributed as tdist
 import delayrepay_b200 as dr
-from delayrepay_b200 import dist as dd, workloads as wl
+from delayrepay_b200 import dist as dd
+import workloads as wl
 from delayrepay_b200._lib import lib, check
 
 rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
