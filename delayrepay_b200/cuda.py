@@ -24,7 +24,43 @@ def is_ndarray(arr):
 
 
 def run(ex):
+    """Backend protocol entry (reference delayarray.py:43 -> cuda.py:91-96).  ``ex`` is normally
+    one of this package's nodes; a node built by the REFERENCE's own front-end (this module
+    dropped in as ``delayrepay/cuda.py`` under the unmodified reference ``delayarray.py``) is
+    translated first, see ``import_foreign``."""
+    from .delayarray import DelayArray
+    if not isinstance(ex, DelayArray):
+        return import_foreign(ex)._force()
     return engine.run(ex)
+
+
+def import_foreign(ex, _memo=None):
+    """Reference front-end node -> engine node, by the attributes the reference's own emitter
+    reads (cuda.py:55-84): ``NPArray.array``, ``Scalar.val``, ``.func`` + ``.children`` of
+    BinaryNumpyEx / UnaryFuncEx / BinaryFuncEx, ``NPRef.ref``.  A node the reference has already
+    evaluated (``self.array`` cached, delayarray.py:38-44) enters as a leaf.  Unknown node
+    classes raise NotImplementedError (the reference emitter returns NotImplemented for
+    ReduceEx / NPRef, cuda.py:80-88)."""
+    from . import delayarray as da
+    memo = {} if _memo is None else _memo
+    hit = memo.get(id(ex))
+    if hit is not None:
+        return hit
+    name = type(ex).__name__
+    if isinstance(ex, da.DelayArray):
+        node = ex
+    elif name == "Scalar":
+        node = da.Scalar(ex.val)
+    elif name == "NPRef":
+        node = import_foreign(ex.ref, memo)
+    elif "array" in getattr(ex, "__dict__", {}) and (is_ndarray(ex.array) or isinstance(ex.array, _np.ndarray)):
+        node = da.NPArray(ex.array)
+    elif name in ("BinaryNumpyEx", "UnaryFuncEx", "BinaryFuncEx"):
+        node = da.create_ex(ex.func, [import_foreign(c, memo) for c in ex.children])
+    else:
+        raise NotImplementedError(f"cannot evaluate a foreign {name} node")
+    memo[id(ex)] = node
+    return node
 
 
 def run_many(nodes):
@@ -106,14 +142,79 @@ fallback = types.SimpleNamespace(
 
 
 def _eager(ufunc):
-    def call(a, b):
+    """Eager binary ufunc on backend arrays (what cupy.add etc. are to the reference's broadcast
+    escape, delayarray.py:47-55,189-193): capture + force, returns a backend array."""
+    def call(a, b, *args, **kwargs):
         from .delayarray import arg_to_numpy_ex, create_ex
         return create_ex(ufunc, [arg_to_numpy_ex(a), arg_to_numpy_ex(b)])._force()
+    call.__name__ = ufunc.__name__
     return call
 
 
+def _forced(res):
+    from .delayarray import DelayArray
+    if isinstance(res, DelayArray):
+        return res._force()
+    if isinstance(res, tuple):
+        return tuple(_forced(r) for r in res)
+    return res
+
+
+def _eager_fn(np_func):
+    """Eager array function on backend arrays (cupy.sum, cupy.roll ... in the reference,
+    delayarray.py:511-568,608-615): runs this package's device handler and returns the backend
+    array, so the unmodified reference handlers (`_backend.fallback.sum(arr.__array__(), ...)`)
+    work on top of this module."""
+    def call(*args, **kwargs):
+        from . import delayarray as da
+        lifted = [da.NPArray(a) if isinstance(a, DeviceArray) else a for a in args]
+        return _forced(da.HANDLED_FUNCTIONS[np_func](*lifted, **kwargs))
+    call.__name__ = np_func.__name__
+    return call
+
+
+def _dot(a, b, out=None):
+    from . import delayarray as da
+    left = da.arg_to_numpy_ex(a)
+    return left._dot([left, da.arg_to_numpy_ex(b)])._force()
+
+
+for _name in ("var", "sum", "transpose", "roll", "max", "min", "mean", "average", "repeat", "cumsum",
+              "tile", "diag", "diagflat", "where", "prod", "std", "argmax", "argmin"):
+    setattr(fallback, _name, _eager_fn(getattr(_np, _name)))
+fallback.dot = _dot
+fallback.matmul = _dot
+for _name in ("maximum", "minimum", "greater", "less", "add", "multiply", "subtract", "true_divide"):
+    setattr(fallback, _name, _eager(getattr(_np, _name)))
+fallback.pi = _np.pi
+
+
+def _rand_fn(name):
+    def call(*args, **kwargs):
+        from . import random as _random           # imports this module: resolved at call time
+        return _forced(getattr(_random, name)(*args, **kwargs))
+    call.__name__ = name
+    return call
+
+
+_random_ns = types.SimpleNamespace(**{n: _rand_fn(n) for n in
+                                      ("rand", "randn", "random", "seed", "randint", "choice")})
+fallback.random = _random_ns
+
+
+def _fft_fn(name):
+    def call(a, *args, **kwargs):
+        from . import fft as _fft
+        return getattr(_fft, name)(a, *args, **kwargs)._force()
+    call.__name__ = name
+    return call
+
+
+# `fft.fft` on the backend MODULE itself: reference fft.py:7,12 calls backend.fft.fft(...)
+fft = types.SimpleNamespace(fft=_fft_fn("fft"), ifft=_fft_fn("ifft"))
+fallback.fft = fft
+
 np = types.SimpleNamespace(
     pi=_np.pi, add=_eager(_np.add), multiply=_eager(_np.multiply), subtract=_eager(_np.subtract),
-    true_divide=_eager(_np.true_divide), matmul=lambda a, b: (
-        __import__("delayrepay_b200").delayarray.arg_to_numpy_ex(a) @ b)._force(),
+    true_divide=_eager(_np.true_divide), matmul=_dot, random=_random_ns, fft=fft,
 )

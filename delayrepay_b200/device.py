@@ -317,6 +317,45 @@ class DeviceArray:
         target = self if (isinstance(key, type(Ellipsis)) or key == slice(None)) else self[key]
         engine.assign(target, value)
 
+    # ---- eager operators (what cupy.ndarray offers the reference: results of its broadcast
+    # escape and of fallback.* calls are raw backend arrays that user code goes on computing
+    # with, delayarray.py:47-55,85,513-568).  Each one is capture + force through the engine.
+    def _eager(ufunc, swap=False):                                   # noqa: N805
+        def op(self, other):
+            from .delayarray import DelayArray, NPArray, arg_to_numpy_ex, create_ex
+            if isinstance(other, DelayArray):
+                return NotImplemented                # the lazy operand's reflected operator captures
+            try:
+                rhs = arg_to_numpy_ex(other)
+            except (NotImplementedError, TypeError):
+                return NotImplemented
+            args = [rhs, NPArray(self)] if swap else [NPArray(self), rhs]
+            return create_ex(ufunc, args)._force()
+        return op
+
+    __add__, __radd__ = _eager(np.add), _eager(np.add, True)
+    __sub__, __rsub__ = _eager(np.subtract), _eager(np.subtract, True)
+    __mul__, __rmul__ = _eager(np.multiply), _eager(np.multiply, True)
+    __truediv__, __rtruediv__ = _eager(np.true_divide), _eager(np.true_divide, True)
+    __pow__ = _eager(np.power)
+    __eq__, __ne__ = _eager(np.equal), _eager(np.not_equal)
+    __lt__, __le__ = _eager(np.less), _eager(np.less_equal)
+    __gt__, __ge__ = _eager(np.greater), _eager(np.greater_equal)
+    del _eager
+    __hash__ = object.__hash__
+
+    def __neg__(self):
+        from .delayarray import NPArray, create_ex
+        return create_ex(np.negative, [NPArray(self)])._force()
+
+    def __abs__(self):
+        from .delayarray import NPArray, create_ex
+        return create_ex(np.absolute, [NPArray(self)])._force()
+
+    def sum(self, *args, **kwargs):
+        from .delayarray import NPArray
+        return np.sum(NPArray(self), *args, **kwargs)._force()
+
     def item(self):
         return self.get().item()
 

@@ -259,7 +259,17 @@ class Args:
         return lay[0].pack(*self.vals), lay[1], lay[2]
 
 
+_last_kernel = [None]
+
+
+def last_kernel_name():
+    """Name (dr_<family>_<structural hash>) of the kernel launched last; bench.py ties its ncu
+    traffic figure to it."""
+    return _last_kernel[0]
+
+
 def launch(kernel, dev, grid, block, args, smem=0, stream=0, cluster=1):
+    _last_kernel[0] = kernel.name
     if dev < 0:
         dry_log.append((kernel, grid, block))
         return
