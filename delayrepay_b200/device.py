@@ -375,6 +375,13 @@ class DeviceArray:
         return f"DeviceArray(shape={self.shape}, dtype={self.dtype}, dev={self.dev})"
 
 
+# The reference's front-end recognises a backend array by its class NAME (delayarray.py:224-226:
+# `type(args[0]).__name__ == "ndarray"` keys the memo table by id(array), and NPArray.astype
+# deletes that key, :401-408) -- cupy.ndarray and numpy.ndarray both qualify.  To host the
+# unmodified front-end the backend array class therefore has to be called `ndarray` too.
+DeviceArray.__name__ = "ndarray"
+
+
 def _resolve_shape(size, shape):
     shape = [int(s) for s in shape]
     if shape.count(-1) > 1:
