@@ -348,12 +348,12 @@ def bench_sharded(dr, wl, tm, ver, dev, peak, sync, rank, world, max_over_ranks,
     row blocks, halo rows pushed into the neighbours' memory by the stencil kernel."""
     from oracle import refcpu
     out = {}
-    mesh = dr.shard.init()
+    mesh = dr.sharding.init()
     # ---- C3
     n, chunk = (1 << 30, 1 << 22) if not quick else (1 << 24, 1 << 22)
     loc = wl.make_inputs("l2", chunk, seed=3 + rank)
-    a = dr.shard.from_local(dr.tile(dr.array(loc["a"]), n // chunk))
-    b = dr.shard.from_local(dr.tile(dr.array(loc["b"]), n // chunk))
+    a = dr.sharding.from_local(dr.tile(dr.array(loc["a"]), n // chunk))
+    b = dr.sharding.from_local(dr.tile(dr.array(loc["b"]), n // chunk))
     ms = max_over_ranks(tm.timed(lambda: wl.l2_distance(dr, a, b).run(), 10, 2, sync))
     got = float(wl.l2_distance(dr, a, b))
     tot = 0.0
@@ -375,12 +375,13 @@ def bench_sharded(dr, wl, tm, ver, dev, peak, sync, rank, world, max_over_ranks,
 
     def u0(r0, r1, c0, c1):
         return h0[np.ix_(np.arange(r0, r1) % blk, np.arange(c0, c1) % blk)]
-    u = dr.shard.from_global_fn(lambda r0, r1: dr.tile(dr.array(h0), ((r1 - r0) // blk + 2, g // blk))[
+    u = dr.sharding.from_global_fn(lambda r0, r1: dr.tile(dr.array(h0), ((r1 - r0) // blk + 2, g // blk))[
         (r0 % blk):(r0 % blk) + (r1 - r0)], (g, g), np.float32)
+    assert u.array.base.H == 1
     wl.heat(dr, u, steps)                                   # warm-up = the verified run
     ok = True
     for (r0, r1, c0, c1) in [(lo, min(lo + 64, hi), 0, 96), (max(hi - 64, lo), hi, g - 96, g)]:
-        got = u.local_rows(r0, r1)[:, c0:c1].get()
+        got = u.array.local_rows(r0, r1)[:, c0:c1].get()
         ok &= got.tobytes() == heat_oracle_block(wl, u0, r0, r1, c0, c1, steps, g).tobytes()
     ver.put("sharded_heat_x100", ok, bar="bit-exact after 100 steps on the first and last 64 rows of this "
             "rank's block (they depend on the neighbours' rows through 100 halo exchanges)")

@@ -11,6 +11,8 @@ from .device import (DeviceArray, set_device, current_device, synchronize,  # no
                      pinned_empty)
 from . import random, fft                   # noqa: F401
 from .stream import map_chunks              # noqa: F401
+from . import sharding                      # noqa: F401
+from .sharding import shard                 # noqa: F401
 
 pi = backend.backend.np.pi
 

@@ -48,6 +48,11 @@ _SIGS = {
     "drc_memcpy_d2d_async": ([i32, i32, u64, u64, sz], i32),
     "drc_memcpy_peer_async": ([i32, u64, i32, u64, sz, i32, i32], i32),
     "drc_enable_peer_access": ([i32, i32], i32),
+    "drc_peer_alloc": ([i32, sz, P(u64)], i32),
+    "drc_peer_free": ([i32, u64], i32),
+    "drc_ipc_get_handle": ([i32, u64, vp], i32),
+    "drc_ipc_open_handle": ([i32, vp, P(u64)], i32),
+    "drc_ipc_close_handle": ([i32, u64], i32),
     "drc_host_alloc": ([sz, P(vp)], i32),
     "drc_host_free": ([vp], i32),
     "drc_host_register": ([vp, sz], i32),

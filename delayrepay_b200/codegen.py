@@ -999,7 +999,44 @@ def gen_cols(name, prog, in_class, reduce, threads=256, V=1, partial=False):
 
 
 # --------------------------------------------------------------------------- stencil family
-def gen_stencil(name, prog, roles, out_dt, TW=248, TH=32, NS=4, threads=992):
+# Device helpers of the halo-pushing stencil variant.  They live here and not in prelude.cuh so
+# that the text (and with it the cubin cache key) of every other kernel stays what it was.
+HALO_HELPERS = r"""
+// Row-sharded stencils (sharding.py): a kernel stores its boundary rows straight into the
+// neighbour GPU's block (NVLink peer mapping) and then publishes the step number with a
+// system-scope release store; the neighbour's next step acquires it before its TMA unit reads
+// the halo rows.  No NCCL, no host round trip, nothing but the fused kernel on the stream.
+__device__ __forceinline__ unsigned dr_ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void dr_st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long dr_globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// Spin until *flag has reached step `want` (wrap-safe).  A neighbour that never signals (its
+// process died) must not hang the GPU: trap after 20 s.
+__device__ __forceinline__ void dr_wait_epoch(const unsigned* flag, unsigned want) {
+  unsigned long long t0 = 0;
+  while ((int)(dr_ld_acquire_sys(flag) - want) < 0) {
+    __nanosleep(100);
+    const unsigned long long now = dr_globaltimer();
+    if (t0 == 0) t0 = now;
+    else if (now - t0 > 20000000000ull) __trap();
+  }
+  // the halo rows were written by another GPU (generic proxy); the TMA unit reads them through
+  // the async proxy
+  asm volatile("fence.proxy.async;" ::: "memory");
+}
+"""
+
+
+def gen_stencil(name, prog, roles, out_dt, TW=248, TH=32, NS=4, threads=992, halo=False):
     """Shifted-view stencil over ONE 2-d base array, written to a fresh copy of the base
     (ping-pong: Jacobi semantics without the reference's temporary + copy, delayarray.py:114-121).
 
@@ -1011,7 +1048,17 @@ def gen_stencil(name, prog, roles, out_dt, TW=248, TH=32, NS=4, threads=992):
     boxes is filled by cp.async.bulk.tensor.2d + mbarrier so the load of tile t+NS-1 overlaps the
     arithmetic of tile t.  Each thread produces 4 consecutive cells (one 128-bit store) per row
     pass through the lockstep / packed-f32x2 body.  Cells of the base outside the assigned view
-    are copied through unchanged."""
+    are copied through unchanged.
+
+    ``halo=True`` (row-sharded arrays, sharding.py): the block carries H halo rows on each side
+    that belong to the neighbour ranks.  The kernel then (i) walks the tile rows that contain
+    its first / last H owned rows FIRST, stores those rows a second time into the neighbour
+    GPU's block (peer-mapped memory over NVLink) and, when the last such tile has finished,
+    publishes the step number to the neighbour with a system-scope release store; (ii) before
+    the TMA load of any tile whose box touches a halo row, acquires the step number the
+    neighbour published in the previous step; (iii) never writes its own halo rows (the
+    neighbours do).  The exchange is therefore part of the stencil kernel: boundary rows travel
+    while the interior is being computed, and nothing else is on the stream."""
     TW = int(os.environ.get("DR_ST_TW", TW))
     TH = int(os.environ.get("DR_ST_TH", TH))
     NS = int(os.environ.get("DR_ST_NS", NS))
@@ -1043,6 +1090,14 @@ def gen_stencil(name, prog, roles, out_dt, TW=248, TH=32, NS=4, threads=992):
       f"i64 gs_row[{max(len(arrays), 1)}]; i64 gs_col[{max(len(arrays), 1)}]; }};")
     params = [f"const __grid_constant__ DrTensorMap tmap", f"const Geo_{name} g",
               f"const {T}* __restrict__ base", f"{T}* __restrict__ out"]
+    if halo:
+        w(HALO_HELPERS)
+        # up = the neighbour that owns the rows above this block, dn = below.  peer_*_rows: where
+        # my first / last H owned rows go in THEIR output block; peer_*_flag: their "from below" /
+        # "from above" flag; my_flag_*: mine; cnt: two tile counters in my memory.
+        w(f"struct Halo_{name} {{ unsigned long long peer_up_rows, peer_dn_rows, peer_up_flag, peer_dn_flag, "
+          f"my_flag_up, my_flag_dn, cnt; unsigned epoch; int H, n_up_tiles, n_dn_tiles, nprio; int prio[4]; }};")
+        params.append(f"const Halo_{name} hx")
     for i, a in enumerate(arrays):
         params.append(f"const char* __restrict__ in{i}")
     for j, (_, dt) in enumerate(scalars):
@@ -1066,9 +1121,25 @@ def gen_stencil(name, prog, roles, out_dt, TW=248, TH=32, NS=4, threads=992):
             w("  __shared__ float2 dr_erf_tab[DR_ERF_TAB_PAIRS];")
             w("  dr_erf_tab_stage(dr_erf_tab);")
     w(f"  const int tx = tid % {cols_per_row}, ty = tid / {cols_per_row};")
+    if halo:
+        w("  const bool has_up = hx.peer_up_rows != 0ull, has_dn = hx.peer_dn_rows != 0ull;")
+        w("  bool up_ok = !has_up, dn_ok = !has_dn;")
+        w("  const int own_lo = hx.H, own_hi = g.rows - hx.H;          // owned rows [own_lo, own_hi)")
+        # boundary tile rows first: hx.prio (sorted) lists them, the rest follow in order
+        w("  auto tile_row = [&](int trow) {")
+        w("    if (trow < hx.nprio) return hx.prio[trow];")
+        w("    int by = trow - hx.nprio;")
+        w("    for (int k = 0; k < hx.nprio; ++k) by += (by >= hx.prio[k]);")
+        w("    return by;")
+        w("  };")
     w("  auto issue = [&](int tile, int stage) {")
     w("    if (tile < g.ntiles) {")
-    w(f"      const int by = tile / g.tiles_x, bx = tile - by * g.tiles_x;")
+    if halo:
+        w("      const int trow = tile / g.tiles_x, bx = tile - trow * g.tiles_x, by = tile_row(trow);")
+        w(f"      if (!up_ok && by * {TH} - {hu} < own_lo) {{ dr_wait_epoch(reinterpret_cast<const unsigned*>(hx.my_flag_up), hx.epoch - 1u); up_ok = true; }}")
+        w(f"      if (!dn_ok && by * {TH} + {TH + hd} > own_hi) {{ dr_wait_epoch(reinterpret_cast<const unsigned*>(hx.my_flag_dn), hx.epoch - 1u); dn_ok = true; }}")
+    else:
+        w(f"      const int by = tile / g.tiles_x, bx = tile - by * g.tiles_x;")
     w(f"      dr_mbar_expect_tx(&bar[stage], {stage_bytes});")
     w(f"      dr_tma_load_2d(dr_smem + stage * {stage_bytes_al}, &tmap, bx * {TW} - {hl_pad}, by * {TH} - {hu}, &bar[stage]);")
     w("    }")
@@ -1080,7 +1151,12 @@ def gen_stencil(name, prog, roles, out_dt, TW=248, TH=32, NS=4, threads=992):
     w(f"    if (tid == 0) issue(tile + {NS - 1} * gridDim.x, (it + {NS - 1}) % {NS});")
     w(f"    dr_mbar_wait(&bar[stage], (it / {NS}) & 1);")
     w(f"    const {T}* sm = reinterpret_cast<const {T}*>(dr_smem + stage * {stage_bytes_al});")
-    w("    const int by = tile / g.tiles_x, bx = tile - by * g.tiles_x;")
+    if halo:
+        w("    const int trow = tile / g.tiles_x, bx = tile - trow * g.tiles_x, by = tile_row(trow);")
+        w(f"    const bool push_up = has_up && by * {TH} < own_lo + hx.H && by * {TH} + {TH} > own_lo;")
+        w(f"    const bool push_dn = has_dn && by * {TH} < own_hi && by * {TH} + {TH} > own_hi - hx.H;")
+    else:
+        w("    const int by = tile / g.tiles_x, bx = tile - by * g.tiles_x;")
     w(f"    const int gx = bx * {TW} + tx * {V};")
     w("#pragma unroll")
     w(f"    for (int pass = 0; pass < {TH // rows_per_pass}; ++pass) {{")
@@ -1152,13 +1228,41 @@ def gen_stencil(name, prog, roles, out_dt, TW=248, TH=32, NS=4, threads=992):
     w("          const int x = gx + e;")
     w("          if (!(row_in && x >= g.c0 && x < g.c0 + g.w)) r0.v[e] = keep.v[e];")
     w("        }")
-    w(f"        dr_st<true, {T}, {V}>(out + (i64)gy * g.pitch_elems + gx, r0);")
+    if halo:
+        # halo rows belong to the neighbours (they store them); my first / last H owned rows are
+        # stored twice: into my block and into the neighbour's
+        w("        if (!((has_up && gy < own_lo) || (has_dn && gy >= own_hi)))")
+        w(f"          dr_st<true, {T}, {V}>(out + (i64)gy * g.pitch_elems + gx, r0);")
+        w("        if (push_up && gy >= own_lo && gy < own_lo + hx.H)")
+        w(f"          dr_st<false, {T}, {V}>(reinterpret_cast<{T}*>(hx.peer_up_rows) + (i64)(gy - own_lo) * g.pitch_elems + gx, r0);")
+        w("        if (push_dn && gy >= own_hi - hx.H && gy < own_hi)")
+        w(f"          dr_st<false, {T}, {V}>(reinterpret_cast<{T}*>(hx.peer_dn_rows) + (i64)(gy - (own_hi - hx.H)) * g.pitch_elems + gx, r0);")
+    else:
+        w(f"        dr_st<true, {T}, {V}>(out + (i64)gy * g.pitch_elems + gx, r0);")
     w("      }")
     w("    }")
+    if halo:
+        w("    if (push_up || push_dn) __threadfence_system();      // my peer stores before the flag")
     w("    __syncthreads();")
+    if halo:
+        # the last boundary tile to finish publishes this step to the neighbour; by then every
+        # tile that read the halo rows on that side has consumed them (same tiles), so the
+        # neighbour may overwrite them in ITS next step
+        w("    if (tid == 0 && (push_up || push_dn)) {")
+        w("      unsigned* cnt = reinterpret_cast<unsigned*>(hx.cnt);")
+        w("      __threadfence_system();")
+        w("      if (push_up && atomicAdd(&cnt[0], 1u) == (unsigned)hx.n_up_tiles - 1u) {")
+        w("        cnt[0] = 0u; __threadfence_system();")
+        w("        dr_st_release_sys(reinterpret_cast<unsigned*>(hx.peer_up_flag), hx.epoch);")
+        w("      }")
+        w("      if (push_dn && atomicAdd(&cnt[16], 1u) == (unsigned)hx.n_dn_tiles - 1u) {")
+        w("        cnt[16] = 0u; __threadfence_system();")
+        w("        dr_st_release_sys(reinterpret_cast<unsigned*>(hx.peer_dn_flag), hx.epoch);")
+        w("      }")
+        w("    }")
     w("  }")
     w("}")
-    meta = dict(TW=TW, TH=TH, NS=NS, BW=BW, BH=BH, hl_pad=hl_pad, hu=hu, smem=NS * stage_bytes_al,
+    meta = dict(TW=TW, TH=TH, NS=NS, BW=BW, BH=BH, hl_pad=hl_pad, hu=hu, hd=hd, smem=NS * stage_bytes_al,
                 threads=threads)
     return "\n".join(src) + "\n", meta
 

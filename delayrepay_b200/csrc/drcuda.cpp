@@ -46,6 +46,7 @@ int fail(const char* fmt, ...) {
   X(cuMemAllocAsync) X(cuMemFreeAsync) X(cuDeviceGetDefaultMemPool) X(cuMemPoolSetAttribute) \
   X(cuMemPoolTrimTo) X(cuMemsetD8Async) X(cuMemcpyHtoDAsync) X(cuMemcpyDtoHAsync)            \
   X(cuMemcpyDtoDAsync) X(cuMemcpyPeerAsync) X(cuCtxEnablePeerAccess)                         \
+  X(cuMemAlloc) X(cuMemFree) X(cuIpcGetMemHandle) X(cuIpcOpenMemHandle) X(cuIpcCloseMemHandle) \
   X(cuDeviceCanAccessPeer) X(cuMemHostAlloc) X(cuMemFreeHost) X(cuMemHostRegister)           \
   X(cuMemHostUnregister) X(cuModuleLoadData) X(cuModuleUnload) X(cuModuleGetFunction)        \
   X(cuFuncSetAttribute) X(cuFuncGetAttribute) X(cuOccupancyMaxActiveBlocksPerMultiprocessor) \
@@ -319,6 +320,46 @@ int drc_enable_peer_access(int dev, int peer) {
   CUresult r = p_cuCtxEnablePeerAccess(g_devs[peer].ctx, 0);
   if (r != CUDA_SUCCESS && r != CUDA_ERROR_PEER_ACCESS_ALREADY_ENABLED)
     return cu_fail(r, "cuCtxEnablePeerAccess");
+  return 0;
+}
+
+// ---- peer-visible allocations (sharded arrays).  cuMemAlloc memory -- unlike stream-ordered
+// pool memory -- is covered by cuCtxEnablePeerAccess inside one process and can be exported to
+// the other ranks' processes with the legacy IPC handles.
+int drc_peer_alloc(int dev, size_t bytes, uint64_t* dptr) {
+  USE(dev);
+  CUdeviceptr p = 0;
+  CU(p_cuMemAlloc(&p, bytes ? bytes : 1));
+  *dptr = (uint64_t)p;
+  return 0;
+}
+
+int drc_peer_free(int dev, uint64_t dptr) {
+  USE(dev);
+  CU(p_cuMemFree((CUdeviceptr)dptr));
+  return 0;
+}
+
+int drc_ipc_get_handle(int dev, uint64_t dptr, void* handle64) {
+  USE(dev);
+  static_assert(sizeof(CUipcMemHandle) == DRC_IPC_HANDLE_BYTES, "CUipcMemHandle is 64 bytes");
+  CU(p_cuIpcGetMemHandle((CUipcMemHandle*)handle64, (CUdeviceptr)dptr));
+  return 0;
+}
+
+int drc_ipc_open_handle(int dev, const void* handle64, uint64_t* dptr) {
+  USE(dev);
+  CUipcMemHandle h;
+  memcpy(&h, handle64, sizeof h);
+  CUdeviceptr p = 0;
+  CU(p_cuIpcOpenMemHandle(&p, h, CU_IPC_MEM_LAZY_ENABLE_PEER_ACCESS));
+  *dptr = (uint64_t)p;
+  return 0;
+}
+
+int drc_ipc_close_handle(int dev, uint64_t dptr) {
+  USE(dev);
+  CU(p_cuIpcCloseMemHandle((CUdeviceptr)dptr));
   return 0;
 }
 

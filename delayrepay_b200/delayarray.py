@@ -281,7 +281,10 @@ class DelayArray(numpy.lib.mixins.NDArrayOperatorsMixin):
             from . import extras
             src = self._force()
             return NPArray(extras.compress(src, ia) if ia.dtype == np.dtype(bool) else extras.take(src, ia))
-        return NPArray(self._force()[key])
+        got = self._force()[key]
+        if hasattr(got, "materialise"):          # one row of a sharded array: replicated on read
+            got = got.materialise()
+        return NPArray(got)
 
     def __setitem__(self, key, item):
         ia = _index_array(key)
@@ -552,6 +555,12 @@ def _leaf_sig(leaf):
     if c is not None and c[0] is arr:
         return c[1]
     if not isinstance(arr, DeviceArray):
+        if getattr(arr, "_is_shard_view", False):
+            # sharded leaf: identity of the viewed rows; keys the sharding layer's own plans
+            # (engine plans are only ever made for the localised expressions)
+            sig = ("SL",) + arr.layout_key()
+            leaf._psig_cache = (leaf.array, sig)
+            return sig
         arr = leaf.__dict__.get("_dev")
         if arr is None:
             return None
@@ -608,6 +617,17 @@ def _plan_info(tag, kids):
     return hash(tuple(parts)), ops
 
 
+def _inherit_mesh(node, kids):
+    """Nodes above a sharded leaf (sharding.py) carry its mesh; engine.run hands them to the
+    sharding layer, which localises the expression per row block."""
+    for k in kids:
+        d = k.__dict__
+        m = d.get("_mesh")
+        if m is not None and not d.get("_replicated"):
+            node._mesh = m
+            return
+
+
 class _Elementwise(NumpyEx, Funcable):
     """Shared body of the three elementwise node classes."""
 
@@ -630,6 +650,7 @@ class _Elementwise(NumpyEx, Funcable):
                     break
         self.shape = shp
         self._psig, self._pops = _plan_info((self.op, self.loop, shp), kids)
+        _inherit_mesh(self, kids)
 
     @classmethod
     def _memo_key(cls, func, *kids):
@@ -677,6 +698,7 @@ class WhereEx(NumpyEx):
         self.loop, self.dtype = (np.dtype(bool), out, out), out
         self.shape = np.broadcast_shapes(cond.shape, a.shape, b.shape)
         self._psig, self._pops = _plan_info(("where", self.loop, self.shape), self.children)
+        _inherit_mesh(self, self.children)
 
     @classmethod
     def _memo_key(cls, *kids):
@@ -710,6 +732,7 @@ class CastEx(NumpyEx):
         self.loop = (src,)
         self.shape = arg.shape
         self._psig, self._pops = _plan_info(("cast", self.loop, self.dtype, self.shape), self.children)
+        _inherit_mesh(self, self.children)
 
     @classmethod
     def _memo_key(cls, arg, dtype):
@@ -744,6 +767,7 @@ class RawOp(NumpyEx):
         self.loop = (arg.dtype,)
         self.dtype = arg.dtype
         self.shape = arg.shape
+        _inherit_mesh(self, self.children)
 
     @classmethod
     def _memo_key(cls, op, arg):
@@ -767,6 +791,7 @@ class ReduceEx(NumpyEx, Funcable):
         self.children = [arg]
         self.post = post
         _register_consumer(arg, self)
+        _inherit_mesh(self, self.children)
         nd = arg.ndim
         if axis is None:
             axes = tuple(range(nd))
@@ -779,6 +804,8 @@ class ReduceEx(NumpyEx, Funcable):
                 axes = tuple(sorted(_normalize_axes(axis, nd)))
         self.axes = axes
         self.keepdims = keepdims
+        if 0 in axes and self.__dict__.get("_mesh") is not None:
+            self._replicated = True          # rows reduced away: the all-reduced result is replicated
         self.shape = tuple((1 if i in axes else s) for i, s in enumerate(arg.shape)
                            if keepdims or i not in axes)
         src = arg.dtype
@@ -810,6 +837,7 @@ class _Contraction(NumpyEx, Funcable):
         self.arg1, self.arg2 = arg1, arg2
         self.children = [arg1, arg2]
         _register_consumer(arg1, self)
+        _inherit_mesh(self, self.children)
         self.dtype = np.result_type(arg1.dtype, arg2.dtype)
         if self.dtype.kind not in "f":
             self.dtype = np.result_type(self.dtype)      # integer dot keeps the integer type
@@ -828,6 +856,8 @@ class DotEx(_Contraction):
             raise ValueError(f"shapes {left.shape} and {right.shape} not aligned")
         super().__init__(left, right)
         self.shape = ()
+        if self.__dict__.get("_mesh") is not None:
+            self._replicated = True
 
     @property
     def name(self):
@@ -870,7 +900,9 @@ class NPArray(NumpyEx):
 
     def __init__(self, array):
         super().__init__()
-        if not isinstance(array, (DeviceArray, np.ndarray)):
+        if getattr(array, "_is_shard_view", False):
+            self._mesh = array.mesh              # a row-sharded array (sharding.py)
+        elif not isinstance(array, (DeviceArray, np.ndarray)):
             array = np.asarray(array)
         if array.dtype.kind not in "biufc":      # complex: storage only (fft results)
             raise TypeError(f"dtype {array.dtype} is not supported on the device")
@@ -880,7 +912,7 @@ class NPArray(NumpyEx):
 
     @classmethod
     def _memo_key(cls, array):
-        if isinstance(array, DeviceArray):
+        if isinstance(array, DeviceArray) or getattr(array, "_is_shard_view", False):
             return ("NPArray",) + array.layout_key()      # the same slice twice is one leaf
         if isinstance(array, np.ndarray):
             # reference: id(array), :225-226 (tests/test.py:145-149 wants NPArray(a) is NPArray(a)).
@@ -892,7 +924,7 @@ class NPArray(NumpyEx):
 
     def _force(self):
         arr = self.array
-        if not isinstance(arr, DeviceArray):
+        if not isinstance(arr, DeviceArray) and not getattr(arr, "_is_shard_view", False):
             dev = self.__dict__.get("_dev")
             if dev is None:
                 dev = self._dev = DeviceArray.from_host(arr)

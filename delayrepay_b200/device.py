@@ -69,11 +69,19 @@ class DeviceBuffer:
     view holds the buffer object, never the raw pointer.  ``version`` counts in-place writes
     so memoised results that read this buffer can tell they are stale."""
 
-    __slots__ = ("ptr", "nbytes", "dev", "version", "__weakref__")
+    __slots__ = ("ptr", "nbytes", "dev", "version", "kind", "halo", "__weakref__")
 
-    def __init__(self, nbytes, dev=None):
+    def __init__(self, nbytes, dev=None, kind="pool", ptr=None):
+        """kind: "pool" (stream-ordered pool allocation, the default), "peer" (cuMemAlloc memory
+        other GPUs can map: blocks of sharded arrays) or "foreign" (a neighbour's allocation
+        mapped into this process; not owned).  ``halo``: the sharding layer's link to the
+        ping-pong partner block and to the neighbours (None for ordinary arrays)."""
         self.nbytes = int(nbytes)
         self.version = 0
+        self.kind, self.halo = kind, None
+        if kind == "foreign":
+            self.dev, self.ptr = dev, int(ptr)
+            return
         if _current["dry"]:
             # planning / compile-only mode (no GPU): a 256-byte aligned placeholder address
             # that is never dereferenced and never freed
@@ -84,14 +92,21 @@ class DeviceBuffer:
         _lib.init()
         self.dev = current_device() if dev is None else dev
         p = C.c_uint64()
-        check(lib.drc_malloc_async(self.dev, 0, self.nbytes, C.byref(p)))
+        if kind == "peer":
+            check(lib.drc_peer_alloc(self.dev, self.nbytes, C.byref(p)))
+        else:
+            check(lib.drc_malloc_async(self.dev, 0, self.nbytes, C.byref(p)))
         self.ptr = p.value
 
     def __del__(self):
         ptr, self.ptr = getattr(self, "ptr", 0), 0
-        if ptr and lib is not None and getattr(self, "dev", -1) >= 0:
+        kind = getattr(self, "kind", "pool")
+        if ptr and lib is not None and getattr(self, "dev", -1) >= 0 and kind != "foreign":
             try:
-                lib.drc_free_async(self.dev, 0, ptr)
+                if kind == "peer":
+                    lib.drc_peer_free(self.dev, ptr)
+                else:
+                    lib.drc_free_async(self.dev, 0, ptr)
             except Exception:       # interpreter shutdown
                 pass
 

@@ -339,9 +339,9 @@ def run_program(prog, outs, reduce=None, inplace=False):
         widest = max([x.dtype.itemsize for x, c in zip(prog.arrays, lay.in_class) if c == "c"]
                      + [d.itemsize for d in out_dts] + [1])
         vec = max(1, 16 // widest) if lay.vec_ok else 1
-        if smem > 40 * 1024 and dev >= 0 and not kern.meta.get("smem_set"):
+        if smem > 40 * 1024 and dev >= 0 and dev not in kern.meta.setdefault("smem_set_devs", set()):
             check(lib.drc_func_set_max_dynamic_smem(dev, kern.func(dev), smem))
-            kern.meta["smem_set"] = True
+            kern.meta["smem_set_devs"].add(dev)
         grid = _grid_for(kern, dev, threads, -(-lay.total // vec), smem)
     else:
         smem = 0
@@ -572,6 +572,9 @@ def evaluate_nodes(nodes, outs=None, inplace=False):
 def run(node):
     """Backend protocol entry: evaluate one node, return its DeviceArray  (cuda.py:91-96)."""
     kind = node.kind
+    if node.__dict__.get("_mesh") is not None:
+        from . import sharding
+        return sharding.run(node)            # a row-sharded operand below: localise per block
     if kind == "leaf":
         return node._force()
     if kind == "scalar":
@@ -591,7 +594,9 @@ def run_many(nodes):
     """Co-evaluate: elementwise nodes sharing a shape go into ONE multi-output kernel."""
     groups = {}
     for n in nodes:
-        if n.kind == "ewise" and n.__dict__.get("array") is None:
+        if n.__dict__.get("_mesh") is not None:
+            n._force()
+        elif n.kind == "ewise" and n.__dict__.get("array") is None:
             groups.setdefault(tuple(n.shape), [])
             if all(n is not m for m in groups[tuple(n.shape)]):
                 groups[tuple(n.shape)].append(n)
@@ -1056,7 +1061,7 @@ _st_plans = {}
 
 class _StPlan:
     __slots__ = ("kern", "meta", "geo", "grid", "arr_idx", "leaf_sigs", "sc_idx", "sc_dt", "tmaps",
-                 "cols", "rows", "pitch")
+                 "cols", "rows", "pitch", "tiles_x", "max_dy")
 
 
 def _stencil_plan_key(src, target):
@@ -1070,7 +1075,7 @@ def _stencil_plan_key(src, target):
                 return None, None
             lk.append(arr.offset if arr.buf is tb else -1)
     return (src._psig, src.shape, target.offset, target.shape, target.strides, target.dtype.str,
-            tb.nbytes, tuple(lk), target.dev), ops
+            tb.nbytes, tuple(lk), target.dev, tb.halo is not None), ops
 
 
 def _stencil_plan_launch(plan, ops, target):
@@ -1082,7 +1087,12 @@ def _stencil_plan_launch(plan, ops, target):
             return False
         arrays.append(leaf._force())
     buf, dev, m = target.buf, target.dev, plan.meta
-    out = DeviceBuffer(buf.nbytes, dev) if dev >= 0 else DeviceBuffer(buf.nbytes)
+    link = buf.halo
+    if link is not None:
+        link.before_stencil(plan.max_dy)
+        out = link.partner
+    else:
+        out = DeviceBuffer(buf.nbytes, dev) if dev >= 0 else DeviceBuffer(buf.nbytes)
     tmap = plan.tmaps.get(buf.ptr)
     if tmap is None:
         if len(plan.tmaps) >= 8:
@@ -1094,12 +1104,16 @@ def _stencil_plan_launch(plan, ops, target):
     a.raw(plan.geo, 8)
     a.ptr(buf.ptr)
     a.ptr(out.ptr)
+    if link is not None:
+        a.raw(link.kernel_args(plan.rows, plan.pitch, m["TH"], plan.tiles_x), 8)
     for arr in arrays:
         a.ptr(arr.ptr)
     for i, dt in zip(plan.sc_idx, plan.sc_dt):
         a.scalar(ops[i].val, dt)
     launch(plan.kern, dev, plan.grid, m["threads"], a, smem=m["smem"])
     buf.swap_storage(out)
+    if link is not None:
+        link.after_stencil()
     stats["plan_hits"] = stats.get("plan_hits", 0) + 1
     return True
 
@@ -1146,18 +1160,26 @@ def _try_stencil(prog, target, plan_key=None, plan_ops=None):
         return False
     dev = target.dev
     st = dev_state(dev)
-    key = ("stencil", prog.key(), tuple(roles), target.dtype.str)
+    link = buf.halo          # row-sharded block: the kernel also exchanges the halo rows
+    max_dy = max(abs(r[1]) for r in tiles)
+    if link is not None:
+        link.before_stencil(max_dy)
+    halo = link is not None
+    key = ("stencil", prog.key(), tuple(roles), target.dtype.str) + (("halo",) if halo else ())
     meta_box = {}
 
     def gen(name):
-        src, meta = codegen.gen_stencil(name, prog, roles, target.dtype)
+        src, meta = codegen.gen_stencil(name, prog, roles, target.dtype, halo=halo)
         meta_box.update(meta)
         return src
     kern = get_kernel(key, gen, meta_box)
     if not kern.meta:
-        kern.meta.update(codegen.gen_stencil("x", prog, roles, target.dtype)[1])
+        kern.meta.update(codegen.gen_stencil("x", prog, roles, target.dtype, halo=halo)[1])
     m = kern.meta
-    out = DeviceBuffer(buf.nbytes, dev) if dev >= 0 else DeviceBuffer(buf.nbytes)
+    if halo:
+        out = link.partner
+    else:
+        out = DeviceBuffer(buf.nbytes, dev) if dev >= 0 else DeviceBuffer(buf.nbytes)
     tiles_x, tiles_y = -(-cols // m["TW"]), -(-rows // m["TH"])
     a = Args()
     a.raw(encode_tensormap(dev, target.dtype.name, buf.ptr, (cols, rows), (pitch,),
@@ -1173,25 +1195,29 @@ def _try_stencil(prog, target, plan_key=None, plan_ops=None):
     a.raw(geo, 8)
     a.ptr(buf.ptr)
     a.ptr(out.ptr)
+    if halo:
+        a.raw(link.kernel_args(rows, pitch, m["TH"], tiles_x), 8)
     for arr in prog.arrays:
         a.ptr(arr.ptr)
     for val, dt in prog.scalars:
         a.scalar(val, dt)
-    if dev >= 0 and not kern.meta.get("smem_set"):
+    if dev >= 0 and dev not in kern.meta.setdefault("smem_set_devs", set()):
         check(lib.drc_func_set_max_dynamic_smem(dev, kern.func(dev), m["smem"]))
-        kern.meta["smem_set"] = True
+        kern.meta["smem_set_devs"].add(dev)
     per_sm = max(1, min(8, (st.max_smem - 1024) // (m["smem"] + 1024)))
     if dev >= 0:
         per_sm = min(per_sm, kern.blocks_per_sm(dev, m["threads"], m["smem"]))
     grid = min(tiles_x * tiles_y, st.sm_count * per_sm)
     launch(kern, dev, grid, m["threads"], a, smem=m["smem"])
     if plan_key is not None:
-        _stencil_plan_record(plan_key, plan_ops, prog, kern, geo, grid, cols, rows, pitch)
+        _stencil_plan_record(plan_key, plan_ops, prog, kern, geo, grid, cols, rows, pitch, tiles_x, max_dy)
     buf.swap_storage(out)              # `out` now owns the old allocation and frees it (stream-ordered)
+    if halo:
+        link.after_stencil()
     return True
 
 
-def _stencil_plan_record(key, ops, prog, kern, geo, grid, cols, rows, pitch):
+def _stencil_plan_record(key, ops, prog, kern, geo, grid, cols, rows, pitch, tiles_x=0, max_dy=0):
     from .delayarray import _leaf_sig
     arr_idx, leaf_sigs, sc_idx = [], [], []
     for arr in prog.arrays:
@@ -1219,6 +1245,7 @@ def _stencil_plan_record(key, ops, prog, kern, geo, grid, cols, rows, pitch):
     p.arr_idx, p.leaf_sigs, p.sc_idx = tuple(arr_idx), tuple(leaf_sigs), tuple(sc_idx)
     p.sc_dt = tuple(dt for _, dt in prog.scalars)
     p.tmaps, p.cols, p.rows, p.pitch = {}, cols, rows, pitch
+    p.tiles_x, p.max_dy = tiles_x, max_dy
     _st_plans[key] = p
 
 

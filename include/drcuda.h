@@ -58,6 +58,17 @@ int drc_memcpy_d2d_async(int dev, int stream, uint64_t dst, uint64_t src, size_t
 int drc_memcpy_peer_async(int dst_dev, uint64_t dst, int src_dev, uint64_t src, size_t bytes,
                           int stream_dev, int stream);
 int drc_enable_peer_access(int dev, int peer);
+/* Peer-visible device memory for sharded arrays (new; north_star item 4): plain cuMemAlloc
+ * allocations, reachable from the other GPUs of the box either through peer access (one process
+ * driving several devices) or through a 64-byte IPC handle opened by the neighbour rank's process
+ * (one process per GPU).  The stencil kernel stores halo rows and release-flags straight into
+ * memory obtained this way. */
+#define DRC_IPC_HANDLE_BYTES 64
+int drc_peer_alloc(int dev, size_t bytes, uint64_t* dptr);
+int drc_peer_free(int dev, uint64_t dptr);
+int drc_ipc_get_handle(int dev, uint64_t dptr, void* handle64);
+int drc_ipc_open_handle(int dev, const void* handle64, uint64_t* dptr);
+int drc_ipc_close_handle(int dev, uint64_t dptr);
 /* Pinned host staging for the e2e path. */
 int drc_host_alloc(size_t bytes, void** hptr);
 int drc_host_free(void* hptr);

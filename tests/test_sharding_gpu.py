@@ -1,0 +1,209 @@
+"""The leading-axis sharding layer (delayrepay_b200/sharding.py) against the oracle.
+
+In-process meshes whose ranks share ONE device run the whole protocol -- partitioning,
+localisation, the halo-pushing stencil kernel with its release/acquire flags, the partial
+reductions and their combination -- on a single GPU, so these tests run on the 1-GPU test box.
+The SPMD tests (one process per GPU: CUDA IPC mappings, TCP rendezvous, libdrcuda's NCCL
+communicator) need two devices and skip otherwise; bench.py exercises the same path at
+WORLD_SIZE > 1 and verifies its results.
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import workloads as wl
+from oracle import refcpu
+from util import assert_bits_equal
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture()
+def mesh3(gpu):
+    from delayrepay_b200 import sharding
+    m = sharding.init(devices=[0, 0, 0])
+    yield m
+    sharding.shutdown()
+
+
+def _oracle_heat(h, steps, before=None):
+    u = refcpu.leaf(h.copy())
+    if before is not None:
+        before(u)
+    wl.heat(refcpu, u, steps)
+    return u.get()
+
+
+@pytest.mark.parametrize("shape,steps", [((403, 512), 40), ((96, 1024), 7), ((1000, 260), 25)])
+def test_sharded_heat_bit_exact_one_gpu_three_ranks(gpu, mesh3, shape, steps):
+    """C4 through the drop-in API on a sharded array: every step is ONE stencil launch per block,
+    halo rows are pushed by the kernel.  Bit-exact against the oracle (Jacobi semantics)."""
+    from delayrepay_b200 import engine
+    dr = gpu
+    rng = np.random.default_rng(4)
+    h = rng.random(shape, dtype=np.float32)
+    u = dr.shard(h)
+    assert u.array.base.H == 1 and u.shape == shape
+    l0 = engine.stats["launches"]
+    wl.heat(dr, u, steps)
+    assert engine.stats["launches"] - l0 == 3 * steps, "one launch per block per step, nothing else"
+    assert all(l.epoch == steps and not l.dirty for l in u.array.base.links.values())
+    assert_bits_equal(u.get(), _oracle_heat(h, steps), f"heat {shape} x{steps}")
+
+
+def test_sharded_heat_with_boundary_writes_and_fallback_exchange(gpu, mesh3):
+    """Writes that are not the stencil kernel (boundary conditions) leave the neighbours' halo
+    copies stale: the next stencil step starts with the peer-copy exchange."""
+    dr = gpu
+    rng = np.random.default_rng(5)
+    h = rng.random((300, 256), dtype=np.float32)
+
+    def bc(u):
+        u[0, :] = 1.0
+        u[:, -1] = 0.5
+        u[100:200, 3:9] = 0.25          # crosses the block boundary rows 100 / 200
+    u = dr.shard(h)
+    want = refcpu.leaf(h.copy())
+    for _ in range(3):
+        bc(u)
+        bc(want)
+        wl.heat(dr, u, 5)
+        wl.heat(refcpu, want, 5)
+    assert_bits_equal(u.get(), want.get(), "heat with boundary writes")
+
+
+def test_sharded_heat_not_stencil_eligible_shape(gpu, mesh3):
+    """203 columns (not a multiple of the vector width): the blocks take the generic
+    temporary + copy path and the explicit exchange every step -- slow, but exact."""
+    dr = gpu
+    rng = np.random.default_rng(6)
+    h = rng.random((150, 203), dtype=np.float32)
+    u = dr.shard(h)
+    wl.heat(dr, u, 6)
+    assert_bits_equal(u.get(), _oracle_heat(h, 6), "heat 150x203")
+
+
+def test_sharded_wide_stencil_halo2(gpu, mesh3):
+    dr = gpu
+    rng = np.random.default_rng(7)
+    h = rng.random((240, 512), dtype=np.float64)
+
+    def step(u):
+        u[2:-2, 2:-2] = 0.2 * (u[4:, 2:-2] + u[:-4, 2:-2] + u[2:-2, 4:] + u[2:-2, :-4] + u[2:-2, 2:-2])
+    u = dr.shard(h, halo=2)
+    want = refcpu.leaf(h.copy())
+    for _ in range(9):
+        step(u)
+        step(want)
+    assert_bits_equal(u.get(), want.get(), "5-point stencil with 2-row reach, float64")
+    with pytest.raises(ValueError):
+        step(dr.shard(h, halo=1))
+
+
+def test_sharded_reductions_and_elementwise(gpu, mesh3):
+    dr = gpu
+    i = wl.make_inputs("l2", (1 << 18) + 5)
+    a, b = dr.shard(i["a"]), dr.shard(i["b"])
+    ra, rb = refcpu.leaf(i["a"]), refcpu.leaf(i["b"])
+
+    def val(x):
+        return float(x.get()) if hasattr(x, "get") else float(x)
+    for name, fn in (("l2", wl.l2_distance), ("dot", wl.dot)):
+        got, want = float(fn(dr, a, b)), val(fn(refcpu, ra, rb))
+        assert abs(got - want) <= 1e-12 * abs(want), (name, got, want)
+    got, want = float(wl.norm(dr, a)), val(wl.norm(refcpu, ra))
+    assert abs(got - want) <= 1e-12 * abs(want)
+    assert float(np.max(a)) == i["a"].max() and float(np.min(a - b)) == (i["a"] - i["b"]).min()
+    assert abs(float(np.mean(a)) - i["a"].mean()) <= 1e-12
+    e = wl.axpy(dr, 1.5, a, b)
+    assert type(e.array).__name__ == "ShardView"
+    assert_bits_equal(e.get(), 1.5 * i["a"] + i["b"], "sharded axpy")
+    # a replicated (ordinary) operand of the global shape is row-sliced per rank
+    assert_bits_equal((a + dr.array(i["b"])).get(), i["a"] + i["b"], "sharded + replicated")
+    assert_bits_equal((a * i["b"]).get(), i["a"] * i["b"], "sharded * host array")
+    m = np.arange(12.0 * 7).reshape(12, 7)
+    s = dr.shard(m, halo=0)
+    np.testing.assert_array_equal(np.sum(s, axis=1).get(), m.sum(1))
+    np.testing.assert_array_equal(np.sum(s, axis=0).get(), m.sum(0))
+    np.testing.assert_array_equal((s + np.arange(7.0)).get(), m + np.arange(7.0))
+    np.testing.assert_array_equal(s[3:9, 1:5].get(), m[3:9, 1:5])
+    np.testing.assert_array_equal(s[5].get(), m[5])
+
+
+def test_sharded_nbody_matches_unsharded(gpu, mesh3):
+    """C5 on a sharded ``pos``: rows of W are sharded, pos / m are gathered once."""
+    dr = gpu
+    i = wl.make_inputs("nbody", 1536)
+    ref = wl.nbody_acc(dr, dr.array(i["pos"]), dr.array(i["m"])).get()
+    got = wl.nbody_acc(dr, dr.shard(i["pos"], halo=0), dr.array(i["m"])).get()
+    scale = np.abs(ref).max()
+    assert np.max(np.abs(got - ref)) <= 1e-5 * scale
+
+
+SPMD = r"""
+import os, sys
+sys.path.insert(0, {root!r})
+import numpy as np
+import delayrepay_b200 as dr
+from delayrepay_b200 import sharding, engine
+import workloads as wl
+from oracle import refcpu
+rank = int(os.environ["RANK"])
+dr.set_device(int(os.environ["LOCAL_RANK"]))
+mesh = sharding.init()
+assert mesh.spmd and mesh.world == 2
+rng = np.random.default_rng(4)
+h = rng.random((515, 768), dtype=np.float32)
+u = dr.shard(h)
+l0 = engine.stats["launches"]
+wl.heat(dr, u, 60)
+assert engine.stats["launches"] - l0 == 60
+want = refcpu.leaf(h.copy()); wl.heat(refcpu, want, 60)
+assert u.get().tobytes() == want.get().tobytes(), "sharded heat differs"
+u[0, :] = 1.0; want[0, :] = 1.0
+wl.heat(dr, u, 3); wl.heat(refcpu, want, 3)
+assert u.get().tobytes() == want.get().tobytes(), "sharded heat after a boundary write differs"
+i = wl.make_inputs("l2", (1 << 20) + 3)
+a, b = dr.shard(i["a"]), dr.shard(i["b"])
+got = float(wl.l2_distance(dr, a, b)); ref = float(np.sqrt(np.sum((i["a"] - i["b"]) ** 2)))
+assert abs(got - ref) <= 1e-12 * ref, (got, ref)
+got = float(wl.dot(dr, a, b)); ref = float(np.dot(i["a"], i["b"]))
+assert abs(got - ref) <= 1e-12 * abs(ref), (got, ref)
+assert (a * 2 + b).get().tobytes() == (i["a"] * 2 + i["b"]).tobytes()
+j = wl.make_inputs("nbody", 1024)
+ref = wl.nbody_acc(dr, dr.array(j["pos"]), dr.array(j["m"])).get()
+got = wl.nbody_acc(dr, dr.shard(j["pos"], halo=0), dr.array(j["m"])).get()
+assert np.max(np.abs(got - ref)) <= 1e-5 * np.abs(ref).max()
+mesh.barrier()
+sharding.shutdown()
+print("SPMD-OK", rank, flush=True)
+"""
+
+
+def test_spmd_two_processes_two_gpus(gpu, tmp_path):
+    from delayrepay_b200 import _lib
+    if _lib.init() < 2:
+        pytest.skip("needs two GPUs")
+    script = tmp_path / "spmd.py"
+    script.write_text(SPMD.format(root=ROOT))
+    port = 29000 + os.getpid() % 2000
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1",
+                   MASTER_PORT=str(port), PYTHONPATH=ROOT + os.pathsep + os.path.join(ROOT, "tests"))
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    outs = []
+    for p in procs:
+        try:
+            outs.append(p.communicate(timeout=300)[0])
+        except subprocess.TimeoutExpired:
+            for q in procs:
+                q.kill()
+            raise
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0 and f"SPMD-OK {r}" in o, o[-3000:]
