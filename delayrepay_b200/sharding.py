@@ -553,6 +553,8 @@ class ShardView:
         H = base.H
         l0, l1 = i0 + self.r0 - lo + H, i1 + self.r0 - lo + H
         blk = base.blocks[r]
+        if H and (l0 < H or l1 > blk.shape[0] - H):
+            _halo_reads.add(base)             # the caller refreshes stale halo rows before it launches
         if l0 < 0 or l1 > blk.shape[0] or l1 < l0:
             raise NotImplementedError(
                 f"rows {i0 + self.r0}..{i1 + self.r0} are not resident on rank {r} (it holds "
@@ -712,6 +714,21 @@ def replicate(view):
     return out
 
 
+_halo_reads = set()        # bases whose halo rows were addressed since the last _refresh_halos()
+
+
+def _refresh_halos(bases=None):
+    """Peer-copy exchange for every base whose halo rows are about to be read and are stale.
+    Collective: every rank reaches this point with the same set (same program, same state)."""
+    todo = list(_halo_reads if bases is None else bases)
+    if bases is None:
+        _halo_reads.clear()
+    for b in todo:
+        if b.halo_dirty:
+            b.exchange_halos()
+    return todo
+
+
 _replicas = weakref.WeakKeyDictionary()      # DeviceBuffer -> {dev: (version, DeviceArray)}
 
 
@@ -851,11 +868,13 @@ def _run_ewise(node):
 def _evaluate_blocks(mesh, node, part, build):
     """One local evaluation per rank (``build(r, i0, i1)`` -> the local lazy node); the fresh
     results become the blocks of a new sharded array -- no copy, plan cache and all."""
+    _halo_reads.clear()
+    lazy = {r: build(r, *part[r]) for r in mesh.local if part[r][1] > part[r][0]}
+    _refresh_halos()
     blocks = {}
     for r in mesh.local:
-        i0, i1 = part[r]
-        if i1 > i0:
-            blocks[r] = build(r, i0, i1)._force()
+        if r in lazy:
+            blocks[r] = lazy[r]._force()
         else:
             dev = mesh.devs[r]
             blocks[r] = DeviceArray.empty((0,) + tuple(node.shape[1:]), node.dtype, dev if dev >= 0 else None)
@@ -878,13 +897,16 @@ def _run_reduce(node):
         return ShardView(_evaluate_blocks(mesh, node, part, lambda r, i0, i1: da.ReduceEx(
             node.func, _localise(child, r, i0, i1, nrows, {"__shape__": child.shape}, mesh),
             node.axes, node.keepdims, node.post)))
-    parts = {}
+    _halo_reads.clear()
+    lazy = {}
     for r in mesh.local:
         i0, i1 = part[r]
         if i1 <= i0:
             raise NotImplementedError(f"rank {r} holds no rows of the reduced array")
         local = _localise(child, r, i0, i1, nrows, {"__shape__": child.shape}, mesh)
-        parts[r] = da.ReduceEx(node.func, local, node.axes, node.keepdims, None)._force()
+        lazy[r] = da.ReduceEx(node.func, local, node.axes, node.keepdims, None)
+    _refresh_halos()
+    parts = {r: n._force() for r, n in lazy.items()}
     mesh.allreduce(parts, node.op)
     res = parts[mesh.local[0]]
     for r in mesh.local[1:]:
@@ -947,10 +969,12 @@ def assign(target, value, drop_row_axis=False):
         key = (node._psig, target.layout_key(), _scalar_sig(node._pops))
         plan = _assign_plans.get(key)
         if plan is not None:
-            _write(base, plan)
+            _refresh_halos(plan[1])
+            _write(base, plan[0])
             return
     nrows = target.shape[0]
     todo = []
+    _halo_reads.clear()
     for r in mesh.local:
         i0, i1 = target.rows_of(r)
         if i1 <= i0:
@@ -973,11 +997,12 @@ def assign(target, value, drop_row_axis=False):
                 loc = _on_device(mesh, arr, mesh.devs[r])
                 vloc = da.NPArray(loc[i0:i1] if full else loc)
         todo.append((tloc, vloc))
+    reads = _refresh_halos()
     _write(base, todo)
     if key is not None:
         if len(_assign_plans) > 256:
             _assign_plans.clear()
-        _assign_plans[key] = todo
+        _assign_plans[key] = (todo, reads)
 
 
 def _write(base, todo):

@@ -100,7 +100,7 @@ def test_sharded_wide_stencil_halo2(gpu, mesh3):
         step(u)
         step(want)
     assert_bits_equal(u.get(), want.get(), "5-point stencil with 2-row reach, float64")
-    with pytest.raises(ValueError):
+    with pytest.raises((ValueError, NotImplementedError)):      # reads 2 rows away, holds 1
         step(dr.shard(h, halo=1))
 
 
@@ -120,7 +120,7 @@ def test_sharded_reductions_and_elementwise(gpu, mesh3):
     assert float(np.max(a)) == i["a"].max() and float(np.min(a - b)) == (i["a"] - i["b"]).min()
     assert abs(float(np.mean(a)) - i["a"].mean()) <= 1e-12
     e = wl.axpy(dr, 1.5, a, b)
-    assert type(e.array).__name__ == "ShardView"
+    assert type(e._force()).__name__ == "ShardView"
     assert_bits_equal(e.get(), 1.5 * i["a"] + i["b"], "sharded axpy")
     # a replicated (ordinary) operand of the global shape is row-sliced per rank
     assert_bits_equal((a + dr.array(i["b"])).get(), i["a"] + i["b"], "sharded + replicated")
@@ -138,10 +138,19 @@ def test_sharded_nbody_matches_unsharded(gpu, mesh3):
     """C5 on a sharded ``pos``: rows of W are sharded, pos / m are gathered once."""
     dr = gpu
     i = wl.make_inputs("nbody", 1536)
-    ref = wl.nbody_acc(dr, dr.array(i["pos"]), dr.array(i["m"])).get()
     got = wl.nbody_acc(dr, dr.shard(i["pos"], halo=0), dr.array(i["m"])).get()
-    scale = np.abs(ref).max()
-    assert np.max(np.abs(got - ref)) <= 1e-5 * scale
+    _check_nbody(i, got)
+
+
+def _check_nbody(i, got):
+    """|error| <= 1e-5 of the term scale sum|w||pos| + |pos| sum|w| against a float64 evaluation
+    (the bar of tests/test_parity_gpu.py: acc is a difference of two large sums)."""
+    p, m = i["pos"].astype(np.float64), i["m"].astype(np.float64)
+    d = p[None, :, :] - p[:, None, :]
+    w = m[None, :] * ((d ** 2).sum(-1) + 1e-3) ** -1.5
+    want = w @ p - p * w.sum(1)[:, None]
+    scale = np.abs(w) @ np.abs(p) + np.abs(p) * np.abs(w).sum(1)[:, None]
+    assert np.max(np.abs(got - want) / scale) <= 1e-5
 
 
 SPMD = r"""
@@ -175,9 +184,13 @@ got = float(wl.dot(dr, a, b)); ref = float(np.dot(i["a"], i["b"]))
 assert abs(got - ref) <= 1e-12 * abs(ref), (got, ref)
 assert (a * 2 + b).get().tobytes() == (i["a"] * 2 + i["b"]).tobytes()
 j = wl.make_inputs("nbody", 1024)
-ref = wl.nbody_acc(dr, dr.array(j["pos"]), dr.array(j["m"])).get()
 got = wl.nbody_acc(dr, dr.shard(j["pos"], halo=0), dr.array(j["m"])).get()
-assert np.max(np.abs(got - ref)) <= 1e-5 * np.abs(ref).max()
+p64, m64 = j["pos"].astype(np.float64), j["m"].astype(np.float64)
+dd = p64[None, :, :] - p64[:, None, :]
+w64 = m64[None, :] * ((dd ** 2).sum(-1) + 1e-3) ** -1.5
+want64 = w64 @ p64 - p64 * w64.sum(1)[:, None]
+scale = np.abs(w64) @ np.abs(p64) + np.abs(p64) * np.abs(w64).sum(1)[:, None]
+assert np.max(np.abs(got - want64) / scale) <= 1e-5
 mesh.barrier()
 sharding.shutdown()
 print("SPMD-OK", rank, flush=True)
