@@ -675,8 +675,12 @@ def replicate(view):
     pieces = {}
     for r in mesh.local:
         i0, i1 = view.rows_of(r)
-        loc = view.local(r, i0, i1)
-        pieces[r] = loc if loc.is_contiguous else loc.copy()
+        if i1 > i0:
+            loc = view.local(r, i0, i1)
+            pieces[r] = loc if loc.is_contiguous else loc.copy()
+        else:
+            dev = mesh.devs[r]
+            pieces[r] = DeviceArray.empty((0,) + tuple(view.shape[1:]), view.dtype, dev if dev >= 0 else None)
     home = mesh.devs[mesh.local[0]]
     total = view.shape[0]
     out = DeviceArray.empty((total,) + row_shape, view.dtype, home if home >= 0 else None)
