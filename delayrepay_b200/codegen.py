@@ -1126,10 +1126,13 @@ def gen_stencil(name, prog, roles, out_dt, TW=248, TH=32, NS=4, threads=992, hal
         w("  bool up_ok = !has_up, dn_ok = !has_dn;")
         w("  const int own_lo = hx.H, own_hi = g.rows - hx.H;          // owned rows [own_lo, own_hi)")
         # boundary tile rows first: hx.prio (sorted) lists them, the rest follow in order
+        # (selects on the four kernel-parameter words: indexing the array would put it on the stack)
+        w("  const int p0 = hx.prio[0], p1 = hx.prio[1], p2 = hx.prio[2], p3 = hx.prio[3], np_ = hx.nprio;")
         w("  auto tile_row = [&](int trow) {")
-        w("    if (trow < hx.nprio) return hx.prio[trow];")
-        w("    int by = trow - hx.nprio;")
-        w("    for (int k = 0; k < hx.nprio; ++k) by += (by >= hx.prio[k]);")
+        w("    if (trow < np_) return trow == 0 ? p0 : trow == 1 ? p1 : trow == 2 ? p2 : p3;")
+        w("    int by = trow - np_;")
+        w("    by += (np_ > 0 && by >= p0); by += (np_ > 1 && by >= p1);")
+        w("    by += (np_ > 2 && by >= p2); by += (np_ > 3 && by >= p3);")
         w("    return by;")
         w("  };")
     w("  auto issue = [&](int tile, int stage) {")
@@ -1145,22 +1148,15 @@ def gen_stencil(name, prog, roles, out_dt, TW=248, TH=32, NS=4, threads=992, hal
     w("    }")
     w("  };")
     w(f"  if (tid == 0) {{ for (int k = 0; k < {NS - 1}; ++k) issue(blockIdx.x + k * gridDim.x, k); }}")
-    w("  int it = 0;")
-    w("  for (int tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x, ++it) {")
-    w(f"    const int stage = it % {NS};")
-    w(f"    if (tid == 0) issue(tile + {NS - 1} * gridDim.x, (it + {NS - 1}) % {NS});")
-    w(f"    dr_mbar_wait(&bar[stage], (it / {NS}) & 1);")
-    w(f"    const {T}* sm = reinterpret_cast<const {T}*>(dr_smem + stage * {stage_bytes_al});")
-    if halo:
-        w("    const int trow = tile / g.tiles_x, bx = tile - trow * g.tiles_x, by = tile_row(trow);")
-        w(f"    const bool push_up = has_up && by * {TH} < own_lo + hx.H && by * {TH} + {TH} > own_lo;")
-        w(f"    const bool push_dn = has_dn && by * {TH} < own_hi && by * {TH} + {TH} > own_hi - hx.H;")
-    else:
-        w("    const int by = tile / g.tiles_x, bx = tile - by * g.tiles_x;")
-    w(f"    const int gx = bx * {TW} + tx * {V};")
-    fast_ok = os.environ.get("DR_ST_NOFAST") is None
+    # Measured (tools/heat_shard_probe.py, 32768^2 float32): the interior variant executes 16
+    # instead of 24 instructions per cell and is SLOWER -- 1.43 ms per step with the row guard kept,
+    # 1.59 ms without it, against 1.31 ms for the general code (= 99 % of the measured copy
+    # bandwidth).  The kernel is not issue-bound; what it needs is the general variant's load /
+    # store interleaving.  The variant stays available for experiments (DR_ST_FAST=1).
+    fast_ok = os.environ.get("DR_ST_FAST") == "1"
+    fast_guard = os.environ.get("DR_ST_FASTGUARD", "1") == "1"
 
-    def emit_passes(inner):
+    def emit_passes(inner, edge=False):
         """The row passes of one tile.  inner=True: the tile lies wholly inside the assigned view
         and inside the array, so every bounds test, the keep/select per cell and the clamping of
         gathered operands are dropped (most tiles; 24 -> 16 instructions per cell for the
@@ -1168,7 +1164,7 @@ def gen_stencil(name, prog, roles, out_dt, TW=248, TH=32, NS=4, threads=992, hal
         w("#pragma unroll")
         w(f"    for (int pass = 0; pass < {TH // rows_per_pass}; ++pass) {{")
         w(f"      const int ly = pass * {rows_per_pass} + ty, gy = by * {TH} + ly;")
-        w("      if (gy < g.rows && gx < g.cols) {" if not inner else "      {")
+        w("      if (gy < g.rows && gx < g.cols) {" if (not inner or fast_guard) else "      {")
         w("        constexpr int u = 0;")
         # gather operands: ONE aligned 128-bit shared load per distinct row offset dy; horizontally
         # shifted views reuse that vector and fetch only the |dx| cells that fall outside it
@@ -1240,7 +1236,7 @@ def gen_stencil(name, prog, roles, out_dt, TW=248, TH=32, NS=4, threads=992, hal
             w("          const int x = gx + e;")
             w("          if (!(row_in && x >= g.c0 && x < g.c0 + g.w)) r0.v[e] = keep.v[e];")
             w("        }")
-        if halo:
+        if halo and edge:
             # halo rows belong to the neighbours (they store them); my first / last H owned rows are
             # stored twice: into my block and into the neighbour's
             w("        if (!((has_up && gy < own_lo) || (has_dn && gy >= own_hi)))")
@@ -1253,33 +1249,61 @@ def gen_stencil(name, prog, roles, out_dt, TW=248, TH=32, NS=4, threads=992, hal
             w(f"        dr_st<true, {T}, {V}>(out + (i64)gy * g.pitch_elems + gx, r0);")
         w("      }")
         w("    }")
-    if fast_ok:
-        w(f"    if (by * {TH} >= g.r0 && by * {TH} + {TH} <= g.r0 + g.h && bx * {TW} >= g.c0 && bx * {TW} + {TW} <= g.c0 + g.w) {{")
-        emit_passes(True)
-        w("    } else {")
-        emit_passes(False)
-        w("    }")
-    else:
-        emit_passes(False)
+
+    def emit_tile(edge):
+        """One trip of the tile loop.  edge=True (halo kernels only): the tile row holds halo rows
+        or rows that are pushed to a neighbour."""
+        w(f"    const int stage = it % {NS};")
+        w(f"    if (tid == 0) issue(tile + {NS - 1} * gridDim.x, (it + {NS - 1}) % {NS});")
+        w(f"    dr_mbar_wait(&bar[stage], (it / {NS}) & 1);")
+        w(f"    const {T}* sm = reinterpret_cast<const {T}*>(dr_smem + stage * {stage_bytes_al});")
+        if halo:
+            w("    const int trow = tile / g.tiles_x, bx = tile - trow * g.tiles_x, by = tile_row(trow);")
+        else:
+            w("    const int by = tile / g.tiles_x, bx = tile - by * g.tiles_x;")
+        if edge:
+            w(f"    const bool push_up = has_up && by * {TH} < own_lo + hx.H && by * {TH} + {TH} > own_lo;")
+            w(f"    const bool push_dn = has_dn && by * {TH} < own_hi && by * {TH} + {TH} > own_hi - hx.H;")
+        w(f"    const int gx = bx * {TW} + tx * {V};")
+        if edge:
+            emit_passes(False, edge=True)
+        elif fast_ok and not halo:
+            w(f"    if (by * {TH} >= g.r0 && by * {TH} + {TH} <= g.r0 + g.h && bx * {TW} >= g.c0 && bx * {TW} + {TW} <= g.c0 + g.w) {{")
+            emit_passes(True)
+            w("    } else {")
+            emit_passes(False)
+            w("    }")
+        else:
+            emit_passes(False)
+        if edge:
+            w("    if (push_up || push_dn) __threadfence_system();      // my peer stores before the flag")
+        w("    __syncthreads();")
+        if edge:
+            # the last boundary tile to finish publishes this step to the neighbour; by then every
+            # tile that read the halo rows on that side has consumed them (same tiles), so the
+            # neighbour may overwrite them in ITS next step
+            w("    if (tid == 0 && (push_up || push_dn)) {")
+            w("      unsigned* cnt = reinterpret_cast<unsigned*>(hx.cnt);")
+            w("      __threadfence_system();")
+            w("      if (push_up && atomicAdd(&cnt[0], 1u) == (unsigned)hx.n_up_tiles - 1u) {")
+            w("        cnt[0] = 0u; __threadfence_system();")
+            w("        dr_st_release_sys(reinterpret_cast<unsigned*>(hx.peer_up_flag), hx.epoch);")
+            w("      }")
+            w("      if (push_dn && atomicAdd(&cnt[16], 1u) == (unsigned)hx.n_dn_tiles - 1u) {")
+            w("        cnt[16] = 0u; __threadfence_system();")
+            w("        dr_st_release_sys(reinterpret_cast<unsigned*>(hx.peer_dn_flag), hx.epoch);")
+            w("      }")
+            w("    }")
+
+    w("  int it = 0, tile = blockIdx.x;")
     if halo:
-        w("    if (push_up || push_dn) __threadfence_system();      // my peer stores before the flag")
-    w("    __syncthreads();")
-    if halo:
-        # the last boundary tile to finish publishes this step to the neighbour; by then every
-        # tile that read the halo rows on that side has consumed them (same tiles), so the
-        # neighbour may overwrite them in ITS next step
-        w("    if (tid == 0 && (push_up || push_dn)) {")
-        w("      unsigned* cnt = reinterpret_cast<unsigned*>(hx.cnt);")
-        w("      __threadfence_system();")
-        w("      if (push_up && atomicAdd(&cnt[0], 1u) == (unsigned)hx.n_up_tiles - 1u) {")
-        w("        cnt[0] = 0u; __threadfence_system();")
-        w("        dr_st_release_sys(reinterpret_cast<unsigned*>(hx.peer_up_flag), hx.epoch);")
-        w("      }")
-        w("      if (push_dn && atomicAdd(&cnt[16], 1u) == (unsigned)hx.n_dn_tiles - 1u) {")
-        w("        cnt[16] = 0u; __threadfence_system();")
-        w("        dr_st_release_sys(reinterpret_cast<unsigned*>(hx.peer_dn_flag), hx.epoch);")
-        w("      }")
-        w("    }")
+        # the boundary tile rows come first in the tile order (tile_row) and have a loop of their
+        # own; the main loop below is the unsharded kernel's, instruction for instruction
+        w("  for (; tile < hx.nprio * g.tiles_x; tile += gridDim.x, ++it) {")
+        emit_tile(True)
+        w("  }")
+    w("  for (; tile < g.ntiles; tile += gridDim.x, ++it) {")
+    emit_tile(False)
     w("  }")
     w("}")
     meta = dict(TW=TW, TH=TH, NS=NS, BW=BW, BH=BH, hl_pad=hl_pad, hu=hu, hd=hd, smem=NS * stage_bytes_al,

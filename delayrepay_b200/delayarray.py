@@ -275,6 +275,32 @@ class DelayArray(numpy.lib.mixins.NDArrayOperatorsMixin):
         return NPArray(self._force().reshape(*args))
 
     def __getitem__(self, key):
+        # views of a LEAF are cached per key: a stencil loop takes the same nine slices every step,
+        # and the cached leaf keeps the whole right-hand side hash-consed (one dict hit per node
+        # instead of a construction).  The views hold the leaf's DeviceBuffer, which survives the
+        # ping-pong swaps; in-place astype() drops the cache.
+        views = self.__dict__.get("_views")
+        if views is not None:
+            try:
+                hit = views.get(key)
+            except TypeError:
+                hit = None
+            if hit is not None:
+                return hit
+        got = self._getitem(key)
+        if self.kind == "leaf" and got.kind == "leaf":
+            try:
+                hash(key)
+            except TypeError:
+                return got
+            if views is None:
+                views = self._views = {}
+            elif len(views) >= 64:
+                views.clear()
+            views[key] = got
+        return got
+
+    def _getitem(self, key):
         ia = _index_array(key)
         if ia is not None:
             # one boolean mask (compaction) or one integer array (gather) along the leading axes
@@ -942,6 +968,7 @@ class NPArray(NumpyEx):
         old_key = self._memo_key(self.array)
         self.array = self.array.astype(dtype)
         self.__dict__.pop("_dev", None)
+        self.__dict__.pop("_views", None)
         self.dtype = self.array.dtype
         if old_key is not None and Memoiser._cache.get(old_key) is self:
             del Memoiser._cache[old_key]

@@ -993,7 +993,7 @@ def assign(target, value):
                               else np.asarray(value))
     if src.kind in ("reduce", "matmul"):
         src = NPArray(src._force())
-    if src.kind != "scalar":
+    if src.kind != "scalar" and tuple(src.shape) != target.shape:
         np.broadcast_shapes(src.shape, target.shape)          # raises on mismatch
         if len(src.shape) > target.ndim or np.broadcast_shapes(src.shape, target.shape) != target.shape:
             raise ValueError(f"could not broadcast input array from shape {src.shape} "
@@ -1006,6 +1006,7 @@ def assign(target, value):
         if st_key is not None:
             plan = _st_plans.get(st_key)
             if plan is not None and _stencil_plan_launch(plan, st_ops, target):
+                plan.keep = src           # keeps the right-hand side hash-consed until the next step
                 target.buf.version += 1
                 return
     prog = planner.build_program([src]) if src.kind != "scalar" else _scalar_program(src)
@@ -1061,7 +1062,7 @@ _st_plans = {}
 
 class _StPlan:
     __slots__ = ("kern", "meta", "geo", "grid", "arr_idx", "leaf_sigs", "sc_idx", "sc_dt", "tmaps",
-                 "cols", "rows", "pitch", "tiles_x", "max_dy")
+                 "cols", "rows", "pitch", "tiles_x", "max_dy", "keep", "layout")
 
 
 def _stencil_plan_key(src, target):
@@ -1099,18 +1100,39 @@ def _stencil_plan_launch(plan, ops, target):
             plan.tmaps.clear()
         tmap = plan.tmaps[buf.ptr] = encode_tensormap(
             dev, target.dtype.name, buf.ptr, (plan.cols, plan.rows), (plan.pitch,), (m["BW"], m["BH"]))
-    a = Args()
-    a.raw(tmap, 64)
-    a.raw(plan.geo, 8)
-    a.ptr(buf.ptr)
-    a.ptr(out.ptr)
-    if link is not None:
-        a.raw(link.kernel_args(plan.rows, plan.pitch, m["TH"], plan.tiles_x), 8)
-    for arr in arrays:
-        a.ptr(arr.ptr)
-    for i, dt in zip(plan.sc_idx, plan.sc_dt):
-        a.scalar(ops[i].val, dt)
-    launch(plan.kern, dev, plan.grid, m["threads"], a, smem=m["smem"])
+    lay = plan.layout
+    if lay is None:
+        a = Args()
+        a.raw(tmap, 64)
+        a.raw(plan.geo, 8)
+        a.ptr(buf.ptr)
+        a.ptr(out.ptr)
+        if link is not None:
+            a.raw(link.kernel_args(plan.rows, plan.pitch, m["TH"], plan.tiles_x), 8)
+        for arr in arrays:
+            a.ptr(arr.ptr)
+        for i, dt in zip(plan.sc_idx, plan.sc_dt):
+            a.scalar(ops[i].val, dt)
+        launch(plan.kern, dev, plan.grid, m["threads"], a, smem=m["smem"])
+        if all(np.dtype(dt).kind == "f" for dt in plan.sc_dt):
+            a.pack()
+            plan.layout = _arg_layouts["".join(a.fmt)]
+    else:
+        # the argument layout never changes for a plan: pack the values straight into it
+        vals = [tmap, plan.geo, buf.ptr, out.ptr]
+        if link is not None:
+            vals.append(link.kernel_args(plan.rows, plan.pitch, m["TH"], plan.tiles_x))
+        for arr in arrays:
+            vals.append(arr.ptr)
+        for i, dt in zip(plan.sc_idx, plan.sc_dt):
+            vals.append(float(dt.type(ops[i].val)))
+        _last_kernel[0] = plan.kern.name
+        if dev >= 0:
+            check(lib.drc_launch_packed(dev, 0, plan.kern.func(dev), plan.grid, 1, 1, m["threads"], 1, 1,
+                                        m["smem"], 1, lay[0].pack(*vals), lay[1], lay[2]))
+            stats["launches"] += 1
+        else:
+            dry_log.append((plan.kern, plan.grid, m["threads"]))
     buf.swap_storage(out)
     if link is not None:
         link.after_stencil()
@@ -1245,7 +1267,7 @@ def _stencil_plan_record(key, ops, prog, kern, geo, grid, cols, rows, pitch, til
     p.arr_idx, p.leaf_sigs, p.sc_idx = tuple(arr_idx), tuple(leaf_sigs), tuple(sc_idx)
     p.sc_dt = tuple(dt for _, dt in prog.scalars)
     p.tmaps, p.cols, p.rows, p.pitch = {}, cols, rows, pitch
-    p.tiles_x, p.max_dy = tiles_x, max_dy
+    p.tiles_x, p.max_dy, p.keep, p.layout = tiles_x, max_dy, None, None
     _st_plans[key] = p
 
 

@@ -338,9 +338,17 @@ class HaloLink:
         dn_rows = self.dn["bufs"][out_idx] if self.dn else 0
         up_flag = self.up["flags"] + 64 if self.up else 0          # their "from below" flag
         dn_flag = self.dn["flags"] if self.dn else 0               # their "from above" flag
+        # tile rows that hold rows pushed to a neighbour (counted for the "boundary done" signal) ...
         up_set = sorted({r // TH for r in range(H, 2 * H)}) if self.up else []
         dn_set = sorted({r // TH for r in range(rows - 2 * H, rows - H)}) if self.dn else []
-        prio = sorted(set(up_set) | set(dn_set))
+        # ... and all tile rows the edge loop must own: those plus the ones holding halo rows
+        # (which this block never writes)
+        edge = set(up_set) | set(dn_set)
+        if self.up:
+            edge |= {r // TH for r in range(0, H)}
+        if self.dn:
+            edge |= {r // TH for r in range(rows - H, rows)}
+        prio = sorted(edge)
         assert len(prio) <= 4
         f = self.flags.ptr
         return struct.pack("<7QI4i4i4x", up_rows, dn_rows, up_flag, dn_flag, f, f + 64, f + 128,
@@ -363,10 +371,11 @@ class ShardedBase:
             tail *= s
         self.pitch = tail * self.dtype.itemsize
         peer = self.H > 0 and mesh.world > 1
+        self._kind = "peer" if (peer and not os.environ.get("DR_SHARD_POOL_MEMORY")) else "pool"   # knob: experiments only
         for r in mesh.local:
             lo, hi = self.bounds[r]
             rows = hi - lo + 2 * self.H
-            buf = DeviceBuffer(rows * self.pitch, mesh.devs[r], kind="peer" if peer else "pool")
+            buf = DeviceBuffer(rows * self.pitch, mesh.devs[r], kind=self._kind)
             self.blocks[r] = DeviceArray(buf, (rows,) + self.gshape[1:], self.dtype)
         if peer:
             self._link_neighbours()
@@ -406,8 +415,8 @@ class ShardedBase:
             blk = self.blocks[r]
             dev = blk.dev
             link = self.links[r] = HaloLink(self, r)
-            link._partner = DeviceBuffer(blk.buf.nbytes, dev, kind="peer")
-            link.flags = DeviceBuffer(_FLAG_BYTES, dev, kind="peer")
+            link._partner = DeviceBuffer(blk.buf.nbytes, dev, kind=self._kind)
+            link.flags = DeviceBuffer(_FLAG_BYTES, dev, kind=self._kind)
             blk.buf.halo = link
             lo, hi = self.bounds[r]
             if hi - lo < 2 * H:
@@ -610,7 +619,20 @@ class ShardView:
         return (off + delta, tuple(view.shape), tuple(view.strides))
 
     def __setitem__(self, key, value):
-        target = self if (key is Ellipsis or (isinstance(key, slice) and key == slice(None))) else self[key]
+        try:
+            target = self._targets.get(key)
+        except (TypeError, AttributeError):
+            target = None
+        if target is None:
+            target = self if (key is Ellipsis or (isinstance(key, slice) and key == slice(None))) else self[key]
+            try:
+                hash(key)
+                if "_targets" not in self.__dict__:
+                    self.__dict__["_targets"] = {}
+                if len(self._targets) < 64:
+                    self._targets[key] = target
+            except TypeError:
+                pass
         if isinstance(target, _RowPick):
             target[...] = value
         elif isinstance(target, DeviceArray):
@@ -975,6 +997,7 @@ def assign(target, value, drop_row_axis=False):
         if plan is not None:
             _refresh_halos(plan[1])
             _write(base, plan[0])
+            plan[2][0] = node             # keeps the global right-hand side hash-consed
             return
     nrows = target.shape[0]
     todo = []
@@ -1006,7 +1029,7 @@ def assign(target, value, drop_row_axis=False):
     if key is not None:
         if len(_assign_plans) > 256:
             _assign_plans.clear()
-        _assign_plans[key] = (todo, reads)
+        _assign_plans[key] = (todo, reads, [node])
 
 
 def _write(base, todo):
