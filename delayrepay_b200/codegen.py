@@ -1387,7 +1387,13 @@ def gen_mm_skinny(name, prog, roles, t_dt, n_out, threads=128, tile_k=256, rows=
         w(f"        {line}")
     root = _store_expr(prog, prog.roots[0], t_dt)
     w(f"        const {T} a_ik = {root};")
-    w(f"#pragma unroll\n        for (int n = 0; n < {n_out}; ++n) acc[r][n] = fma(a_ik, bj[n], acc[r][n]);")
+    if os.environ.get("DR_SK_NOCONTRACT"):
+        # EXPERIMENT (wrong results): the producer alone -- one add per pair keeps it alive, the
+        # n_out contraction FMAs are gone.  full - this = the most a tensor-core contraction could
+        # take off the FP32 pipe (mm_skinny).
+        w("        acc[r][0] += a_ik;")
+    else:
+        w(f"#pragma unroll\n        for (int n = 0; n < {n_out}; ++n) acc[r][n] = fma(a_ik, bj[n], acc[r][n]);")
     w("      }")
     w("    }")
     w("    __syncthreads();")

@@ -389,7 +389,7 @@ _PLAN_LIMIT = 1024
 
 class _Plan:
     __slots__ = ("kern", "grid", "threads", "smem", "head", "arr_idx", "sc_idx", "sc_dt", "leaf_sigs",
-                 "shape", "out_dts", "dev", "scl")
+                 "shape", "out_dts", "dev", "scl", "layout")
 
 
 def _plan_key(nodes):
@@ -432,18 +432,38 @@ def _plan_launch(plan, ops):
                 return None
     dev = plan.dev
     outs = [DeviceArray.empty(plan.shape, dt, dev if dev >= 0 else None) for dt in plan.out_dts]
-    a = Args()
-    if plan.head[0] == "i64":
-        a.i64(plan.head[1])
+    lay = plan.layout
+    if lay is None:
+        a = Args()
+        if plan.head[0] == "i64":
+            a.i64(plan.head[1])
+        else:
+            a.raw(plan.head[1], 8)
+        for arr in arrays:
+            a.ptr(arr.ptr)
+        for i, dt in zip(plan.sc_idx, plan.sc_dt):
+            a.scalar(ops[i].val, dt)
+        for o in outs:
+            a.ptr(o.ptr)
+        launch(plan.kern, dev, plan.grid, plan.threads, a, smem=plan.smem)
+        if all(np.dtype(dt).kind == "f" for dt in plan.sc_dt) and isinstance(plan.grid, int):
+            a.pack()
+            plan.layout = _arg_layouts["".join(a.fmt)]      # the argument layout of a plan is fixed
     else:
-        a.raw(plan.head[1], 8)
-    for arr in arrays:
-        a.ptr(arr.ptr)
-    for i, dt in zip(plan.sc_idx, plan.sc_dt):
-        a.scalar(ops[i].val, dt)
-    for o in outs:
-        a.ptr(o.ptr)
-    launch(plan.kern, dev, plan.grid, plan.threads, a, smem=plan.smem)
+        vals = [plan.head[1]]
+        for arr in arrays:
+            vals.append(arr.buf.ptr + arr.offset)
+        for i, dt in zip(plan.sc_idx, plan.sc_dt):
+            vals.append(float(dt.type(ops[i].val)))
+        for o in outs:
+            vals.append(o.buf.ptr)
+        _last_kernel[0] = plan.kern.name
+        if dev >= 0:
+            check(lib.drc_launch_packed(dev, 0, plan.kern.func(dev), plan.grid, 1, 1, plan.threads, 1, 1,
+                                        plan.smem, 1, lay[0].pack(*vals), lay[1], lay[2]))
+            stats["launches"] += 1
+        else:
+            dry_log.append((plan.kern, plan.grid, plan.threads))
     seen, stamp = set(), []
     for arr in arrays:
         b = arr.buf
@@ -484,8 +504,9 @@ def _plan_record(key, ops, prog, outs, rec):
     p = _Plan()
     p.kern, p.grid, p.threads, p.smem, p.head, p.scl = kern, grid, threads, smem, head, scl
     p.arr_idx, p.leaf_sigs, p.sc_idx = tuple(arr_idx), tuple(leaf_sigs), tuple(sc_idx)
-    p.sc_dt = tuple(dt for _, dt in prog.scalars)
+    p.sc_dt = tuple(np.dtype(dt) for _, dt in prog.scalars)
     p.shape, p.out_dts, p.dev = tuple(outs[0].shape), tuple(o.dtype for o in outs), outs[0].dev
+    p.layout = None
     _plans[key] = p
 
 
