@@ -1095,7 +1095,12 @@ def from_global_fn(fn, gshape, dtype, halo=None, mesh=None, bounds=None):
             rows = fn(a, b)
             if isinstance(rows, da.DelayArray):
                 rows = rows._force()
-            rows = _on_device(mesh, rows, blk.dev) if isinstance(rows, DeviceArray) else np.ascontiguousarray(rows)
+            if isinstance(rows, DeviceArray):
+                rows = _on_device(mesh, rows, blk.dev)
+            elif blk.dev >= 0:
+                rows = DeviceArray.from_host(np.ascontiguousarray(rows, dtype=base.dtype), blk.dev)   # upload to the block's own device
+            else:
+                rows = np.ascontiguousarray(rows)
             engine.assign(blk[a - (lo - H):b - (lo - H)], rows)
         for s0, s1 in ((0, a - (lo - H)), (b - (lo - H), blk.shape[0])):      # unused edge halos
             if s1 > s0:

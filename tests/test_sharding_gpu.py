@@ -153,6 +153,39 @@ def _check_nbody(i, got):
     assert np.max(np.abs(got - want) / scale) <= 1e-5
 
 
+def test_inprocess_mesh_over_two_devices(gpu):
+    """One process driving two GPUs: peer access between the blocks, ncclCommInitAll communicators,
+    grouped all-reduce, peer-copy gather."""
+    from delayrepay_b200 import _lib, sharding
+    if _lib.init() < 2:
+        pytest.skip("needs two GPUs")
+    dr = gpu
+    mesh = sharding.init(devices=[0, 1])
+    try:
+        assert len(mesh.comms) == 2
+        rng = np.random.default_rng(9)
+        h = rng.random((300, 512), dtype=np.float32)
+        u = dr.shard(h)
+        wl.heat(dr, u, 30)
+        u[0, :] = 2.0
+        wl.heat(dr, u, 3)
+        want = refcpu.leaf(h.copy())
+        wl.heat(refcpu, want, 30)
+        want[0, :] = 2.0
+        wl.heat(refcpu, want, 3)
+        assert_bits_equal(u.get(), want.get(), "in-process 2-device heat")
+        i = wl.make_inputs("l2", (1 << 18) + 1)
+        a, b = dr.shard(i["a"]), dr.shard(i["b"])
+        got, ref = float(wl.l2_distance(dr, a, b)), float(np.sqrt(np.sum((i["a"] - i["b"]) ** 2)))
+        assert abs(got - ref) <= 1e-12 * ref
+        assert_bits_equal((a * 2 + b).get(), i["a"] * 2 + i["b"], "in-process 2-device axpy")
+        j = wl.make_inputs("nbody", 1024)
+        _check_nbody(j, wl.nbody_acc(dr, dr.shard(j["pos"], halo=0), dr.array(j["m"])).get())
+    finally:
+        sharding.shutdown()
+        dr.set_device(0)
+
+
 SPMD = r"""
 import os, sys
 sys.path.insert(0, {root!r})
