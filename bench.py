@@ -395,6 +395,28 @@ def bench_sharded(dr, wl, tm, ver, dev, peak, sync, rank, world, max_over_ranks,
         "exchange": "one halo row per neighbour per step, stored into the neighbour's block by the "
                     "stencil kernel over NVLink peer mappings + release/acquire flags (no NCCL, no host sync)",
         "roofline": _hbm_roof(8 * g * (hi - lo), ms / steps, peak, note="per GPU, this rank's rows")}
+    del u
+    # ---- C5: rows of W sharded, pos / m gathered once per step (strong scaling)
+    nb = 65536 if not quick else 8192
+    i = wl.make_inputs("nbody", nb)
+    pos, m = dr.shard(i["pos"], halo=0), dr.array(i["m"])
+    ms = max_over_ranks(tm.timed(lambda: wl.nbody_acc(dr, pos, m).run(), 5, 2, sync))
+    acc = wl.nbody_acc(dr, pos, m)._force()
+    lo, hi = acc.base.bounds[rank]
+    rows = np.arange(lo, hi, max((hi - lo) // 16, 1))
+    got = acc.local_rows(lo, hi).get()[rows - lo]
+    p, mm = i["pos"], i["m"]
+    d = p[None, :, :] - p[rows, None, :]
+    r2 = d[..., 0] ** 2 + d[..., 1] ** 2 + d[..., 2] ** 2 + np.float32(1e-3)
+    w = (mm[None, :] * r2 ** np.float32(-1.5)).astype(np.float64)
+    want = w @ p.astype(np.float64) - p[rows].astype(np.float64) * w.sum(1)[:, None]
+    scale = np.abs(w) @ np.abs(p).astype(np.float64) + np.abs(p[rows]) * np.abs(w).sum(1)[:, None]
+    rel = float(np.max(np.abs(got - want) / scale))
+    ver.put("sharded_nbody", rel <= 1e-5, err_over_term_scale=rel, bar="1e-5 of sum|w||pos| (16 rows of this rank's block, float64 truth)")
+    out["nbody_f32_sharded"] = {
+        "scaling": "strong", "bodies": nb, "rows_per_gpu": hi - lo, "ms": ms, "value": nb * nb / (ms * 1e-3),
+        "unit": "pairs/s", "exchange": "pos columns and the right operand all-gathered per step "
+                                       "(drc_nccl_allgather, 1 MiB); rows of W never leave their GPU"}
     return out
 
 

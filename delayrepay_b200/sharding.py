@@ -910,6 +910,16 @@ def _evaluate_blocks(mesh, node, part, build):
 def _run_reduce(node):
     from . import delayarray as da
     child = node.children[0]
+    if node.op == "sum" and node.axes == (1,) and child.ndim == 2 and not node.keepdims \
+            and child.kind == "ewise" and child.__dict__.get("array") is None:
+        # a pending A @ B over the same lazy producer computes this row sum in the same pass
+        # (the counterpart of the hook in engine._run_reduce)
+        for cons in list(getattr(child, "_consumers", ())):
+            if isinstance(cons, da.MMEx) and cons.arg1 is child and cons.__dict__.get("array") is None \
+                    and cons.shape[1] <= 6:
+                cons._force()
+                if node.__dict__.get("array") is not None:
+                    return node.array
     views = []
     _shard_leaves(child, views, set())
     if not views:                               # the sharded part is behind a cut: already replicated
@@ -967,9 +977,35 @@ def _run_contraction(node):
         b = da.NPArray(replicate(bnode.array))
     nrows = a.shape[0]
     part = _partition(a, va)
-    return ShardView(_evaluate_blocks(mesh, node, part, lambda r, i0, i1: type(node)(
-        _localise(a, r, i0, i1, nrows, {"__shape__": a.shape}, mesh),
-        _localise(b, r, 0, b.shape[0], -1, {"__shape__": b.shape}, mesh))))
+    # a pending A.sum(1) over the same lazy producer (config 5: W @ pos and W.sum(1)) rides along
+    # as a column of ones in the local skinny kernel (engine._try_mm_skinny finds the LOCAL
+    # ReduceEx through the local producer's consumer set), so W is evaluated once per block
+    rowsum = None
+    if isinstance(node, da.MMEx) and a.kind == "ewise" and a.__dict__.get("array") is None:
+        for cons in list(getattr(a, "_consumers", ())):
+            if isinstance(cons, da.ReduceEx) and cons.op == "sum" and cons.axes == (1,) and not cons.keepdims \
+                    and cons.post is None and cons.__dict__.get("array") is None and cons.dtype == node.dtype:
+                rowsum = cons
+                break
+    local_sums = {}
+
+    def build(r, i0, i1):
+        la = _localise(a, r, i0, i1, nrows, {"__shape__": a.shape}, mesh)
+        if rowsum is not None:
+            local_sums[r] = da.ReduceEx(np.add, la, 1, False)        # kept alive until the MMEx ran
+        return type(node)(la, _localise(b, r, 0, b.shape[0], -1, {"__shape__": b.shape}, mesh))
+    base = _evaluate_blocks(mesh, node, part, build)
+    if rowsum is not None and local_sums and all(n.__dict__.get("array") is not None for n in local_sums.values()):
+        blocks = {}
+        for r in mesh.local:
+            if r in local_sums:
+                blocks[r] = local_sums[r].array
+            else:
+                dev = mesh.devs[r]
+                blocks[r] = DeviceArray.empty((0,), rowsum.dtype, dev if dev >= 0 else None)
+        rowsum.array = ShardView(ShardedBase.adopt(mesh, rowsum.shape, rowsum.dtype,
+                                                   [part[r] for r in range(mesh.world)], blocks))
+    return ShardView(base)
 
 
 # ------------------------------------------------------------------------------ assignment
@@ -1053,7 +1089,7 @@ def _write(base, todo):
 def _default_halo(shape, dtype, halo):
     if halo is not None:
         return int(halo)
-    return 1 if (len(shape) == 2 and np.dtype(dtype).kind == "f") else 0
+    return 1 if (len(shape) in (1, 2) and np.dtype(dtype).kind == "f") else 0
 
 
 def shard(x, halo=None, mesh=None):
