@@ -20,7 +20,8 @@ from .device import DeviceArray
 
 
 def is_ndarray(arr):
-    return isinstance(arr, DeviceArray)
+    """A backend array: a DeviceArray, or the row-sharded ShardView of sharding.py."""
+    return isinstance(arr, DeviceArray) or getattr(arr, "_is_shard_view", False) is True
 
 
 def run(ex):

@@ -660,6 +660,13 @@ class ShardView:
         from .delayarray import NPArray, create_ex
         return run(create_ex(np.positive, [NPArray(self)]))
 
+    def astype(self, dtype, copy=True):
+        from .delayarray import CastEx, NPArray
+        dtype = np.dtype(dtype)
+        if dtype == self.dtype:
+            return self.copy() if copy else self
+        return run(CastEx(NPArray(self), dtype))
+
 
 class _RowPick:
     """x[i] / x[i, ...] of a sharded array: one row, owned by one rank.  Assignable; reading it

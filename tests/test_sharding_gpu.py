@@ -134,6 +134,55 @@ def test_sharded_reductions_and_elementwise(gpu, mesh3):
     np.testing.assert_array_equal(s[5].get(), m[5])
 
 
+def test_sharded_numpy_surface(gpu, mesh3):
+    """The NumPy calls a script makes around the hot path, on sharded operands, against NumPy."""
+    dr = gpu
+    rng = np.random.default_rng(12)
+    m, v = rng.standard_normal((50, 12)), rng.standard_normal(50)
+    s, sv = dr.shard(m, halo=0), dr.shard(v, halo=0)
+    w = np.arange(12.0)
+    cases = {
+        "where": (lambda x, y: np.where(x > 0, x, -x), True),
+        "compare": (lambda x, y: x >= 0.5, True),
+        "astype": (lambda x, y: x.astype(np.float32) * 2, True),
+        "pow3": (lambda x, y: x ** 3, True),
+        "mean0": (lambda x, y: np.mean(x, axis=0), False),
+        "max0": (lambda x, y: np.max(x, axis=0), True),
+        "sum1_keepdims": (lambda x, y: np.sum(x, axis=1, keepdims=True), False),
+        "sum_keepdims": (lambda x, y: np.sum(x, keepdims=True), False),
+        "column_broadcast": (lambda x, y: x * y[:, None], True),
+        "neg": (lambda x, y: -x + 1, True),
+        "sqrt_abs": (lambda x, y: np.sqrt(np.abs(x)), True),
+        "min": (lambda x, y: np.min(x), True),
+        "matvec": (lambda x, y: x @ w, False),
+        "norm": (lambda x, y: np.linalg.norm(y), False),
+        "var": (lambda x, y: np.var(y), False),
+        "std": (lambda x, y: np.std(x), False),
+        "any": (lambda x, y: np.any(x > 3), True),
+        "count_nonzero": (lambda x, y: np.count_nonzero(x > 0), True),
+    }
+    for name, (fn, exact) in cases.items():
+        got, want = np.asarray(fn(s, sv).get()), np.asarray(fn(m, v))
+        assert got.shape == want.shape and got.dtype == want.dtype, (name, got.shape, want.shape, got.dtype, want.dtype)
+        if exact:
+            assert_bits_equal(got, want, name)
+        else:
+            np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-13, err_msg=name)
+    s += 1.0                                   # in place: the leaf keeps its blocks
+    assert type(s).__name__ == "NPArray"
+    assert_bits_equal(s.get(), m + 1.0, "in-place add")
+    a, b = s * 2, s + 3
+    dr.evaluate(a, b)
+    assert_bits_equal(a.get(), (m + 1.0) * 2, "evaluate a")
+    assert_bits_equal(b.get(), (m + 1.0) + 3, "evaluate b")
+    assert_bits_equal(s.copy().get(), m + 1.0, "copy")
+    assert len(s) == 50 and s.ndim == 2 and s.size == 600
+    with pytest.raises(NotImplementedError):
+        (s[3:] + s[:-3]).get()                 # rows 3 away are not resident (halo 0)
+    with pytest.raises(AttributeError):
+        np.cumsum(s)                           # not a sharded operation: a clear error, no silent gather
+
+
 def test_sharded_1d_stencil_generic_path(gpu, mesh3):
     """1-d arrays have a halo row too; their stencils take the generic temporary + copy path with
     the peer-copy exchange before each step."""
