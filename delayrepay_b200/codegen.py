@@ -1275,8 +1275,9 @@ def gen_stencil(name, prog, roles, out_dt, TW=248, TH=32, NS=4, threads=992, hal
             w("    }")
         else:
             emit_passes(False)
-        if edge:
-            w("    if (push_up || push_dn) __threadfence_system();      // my peer stores before the flag")
+        # (no per-thread system fence here: the block barrier orders every thread's peer stores
+        # before thread 0, whose own cumulative fence below then orders them before the flag --
+        # 992 MEMBAR.SC.SYS per edge tile cost ~7 us per kernel)
         w("    __syncthreads();")
         if edge:
             # the last boundary tile to finish publishes this step to the neighbour; by then every
