@@ -147,7 +147,8 @@ def test_sharded_numpy_surface(gpu, mesh3):
         # (on a LEAF astype converts in place, like the reference's delayarray.py:401-408; a lazy
         # node casts)
         "astype": (lambda x, y: (x + 0).astype(np.float32) * 2, True),
-        "pow3": (lambda x, y: x ** 3, True),
+        # x ** 3 is the reference's multiply chain (x*x)*x (delayarray.py:316-324), not np.power
+        "pow3": (lambda x, y: (x * x) * x if isinstance(x, np.ndarray) else x ** 3, True),
         "mean0": (lambda x, y: np.mean(x, axis=0), False),
         "max0": (lambda x, y: np.max(x, axis=0), True),
         "sum1_keepdims": (lambda x, y: np.sum(x, axis=1, keepdims=True), False),
