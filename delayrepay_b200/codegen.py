@@ -1096,7 +1096,7 @@ def gen_stencil(name, prog, roles, out_dt, TW=248, TH=32, NS=4, threads=992, hal
         # my first / last H owned rows go in THEIR output block; peer_*_flag: their "from below" /
         # "from above" flag; my_flag_*: mine; cnt: two tile counters in my memory.
         w(f"struct Halo_{name} {{ unsigned long long peer_up_rows, peer_dn_rows, peer_up_flag, peer_dn_flag, "
-          f"my_flag_up, my_flag_dn, cnt; unsigned epoch; int H, n_up_tiles, n_dn_tiles, nprio, main_row0; int prio[4]; }};")
+          f"my_flag_up, my_flag_dn, cnt; unsigned epoch; int H, n_up_tiles, n_dn_tiles, nprio; int prio[4]; }};")
         params.append(f"const Halo_{name} hx")
     for i, a in enumerate(arrays):
         params.append(f"const char* __restrict__ in{i}")
@@ -1125,25 +1125,22 @@ def gen_stencil(name, prog, roles, out_dt, TW=248, TH=32, NS=4, threads=992, hal
         w("  const bool has_up = hx.peer_up_rows != 0ull, has_dn = hx.peer_dn_rows != 0ull;")
         w("  bool up_ok = !has_up, dn_ok = !has_dn;")
         w("  const int own_lo = hx.H, own_hi = g.rows - hx.H;          // owned rows [own_lo, own_hi)")
-        # boundary ("edge") tile rows first: hx.prio lists them (the first rows of the block, then the
-        # last ones); the main rows [main_row0, ...) follow in their natural order, so the main
-        # loop maps tiles exactly like the unsharded kernel, shifted by a constant
-        w("  const int p0 = hx.prio[0], p1 = hx.prio[1], p2 = hx.prio[2], p3 = hx.prio[3];")
-        w("  const int n_edge = hx.nprio * g.tiles_x, main_shift = hx.main_row0 * g.tiles_x - n_edge;")
-        w("  auto edge_row = [&](int trow) { return trow == 0 ? p0 : trow == 1 ? p1 : trow == 2 ? p2 : p3; };")
+        # boundary tile rows first: hx.prio (sorted) lists them, the rest follow in order
+        # (selects on the four kernel-parameter words: indexing the array would put it on the stack)
+        w("  const int p0 = hx.prio[0], p1 = hx.prio[1], p2 = hx.prio[2], p3 = hx.prio[3], np_ = hx.nprio;")
+        w("  auto tile_row = [&](int trow) {")
+        w("    if (trow < np_) return trow == 0 ? p0 : trow == 1 ? p1 : trow == 2 ? p2 : p3;")
+        w("    int by = trow - np_;")
+        w("    by += (np_ > 0 && by >= p0); by += (np_ > 1 && by >= p1);")
+        w("    by += (np_ > 2 && by >= p2); by += (np_ > 3 && by >= p3);")
+        w("    return by;")
+        w("  };")
     w("  auto issue = [&](int tile, int stage) {")
     w("    if (tile < g.ntiles) {")
     if halo:
-        w("      int by, bx;")
-        w("      if (tile < n_edge) {")
-        w("        const int trow = tile / g.tiles_x;")
-        w("        bx = tile - trow * g.tiles_x; by = edge_row(trow);")
-        w(f"        if (!up_ok && by * {TH} - {hu} < own_lo) {{ dr_wait_epoch(reinterpret_cast<const unsigned*>(hx.my_flag_up), hx.epoch - 1u); up_ok = true; }}")
-        w(f"        if (!dn_ok && by * {TH} + {TH + hd} > own_hi) {{ dr_wait_epoch(reinterpret_cast<const unsigned*>(hx.my_flag_dn), hx.epoch - 1u); dn_ok = true; }}")
-        w("      } else {")
-        w("        const int t2 = tile + main_shift;")
-        w("        by = t2 / g.tiles_x; bx = t2 - by * g.tiles_x;")
-        w("      }")
+        w("      const int trow = tile / g.tiles_x, bx = tile - trow * g.tiles_x, by = tile_row(trow);")
+        w(f"      if (!up_ok && by * {TH} - {hu} < own_lo) {{ dr_wait_epoch(reinterpret_cast<const unsigned*>(hx.my_flag_up), hx.epoch - 1u); up_ok = true; }}")
+        w(f"      if (!dn_ok && by * {TH} + {TH + hd} > own_hi) {{ dr_wait_epoch(reinterpret_cast<const unsigned*>(hx.my_flag_dn), hx.epoch - 1u); dn_ok = true; }}")
     else:
         w(f"      const int by = tile / g.tiles_x, bx = tile - by * g.tiles_x;")
     w(f"      dr_mbar_expect_tx(&bar[stage], {stage_bytes});")
@@ -1260,11 +1257,8 @@ def gen_stencil(name, prog, roles, out_dt, TW=248, TH=32, NS=4, threads=992, hal
         w(f"    if (tid == 0) issue(tile + {NS - 1} * gridDim.x, (it + {NS - 1}) % {NS});")
         w(f"    dr_mbar_wait(&bar[stage], (it / {NS}) & 1);")
         w(f"    const {T}* sm = reinterpret_cast<const {T}*>(dr_smem + stage * {stage_bytes_al});")
-        if halo and edge:
-            w("    const int trow = tile / g.tiles_x, bx = tile - trow * g.tiles_x, by = edge_row(trow);")
-        elif halo:
-            w("    const int t2 = tile + main_shift;")
-            w("    const int by = t2 / g.tiles_x, bx = t2 - by * g.tiles_x;")
+        if halo:
+            w("    const int trow = tile / g.tiles_x, bx = tile - trow * g.tiles_x, by = tile_row(trow);")
         else:
             w("    const int by = tile / g.tiles_x, bx = tile - by * g.tiles_x;")
         if edge:
@@ -1306,7 +1300,7 @@ def gen_stencil(name, prog, roles, out_dt, TW=248, TH=32, NS=4, threads=992, hal
     if halo:
         # the boundary tile rows come first in the tile order (tile_row) and have a loop of their
         # own; the main loop below is the unsharded kernel's, instruction for instruction
-        w("  for (; tile < n_edge; tile += gridDim.x, ++it) {")
+        w("  for (; tile < hx.nprio * g.tiles_x; tile += gridDim.x, ++it) {")
         emit_tile(True)
         w("  }")
     w("  for (; tile < g.ntiles; tile += gridDim.x, ++it) {")

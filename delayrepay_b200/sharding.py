@@ -350,15 +350,10 @@ class HaloLink:
             edge |= {r // TH for r in range(rows - H, rows)}
         prio = sorted(edge)
         assert len(prio) <= 4
-        main_row0 = 0                      # edge rows at the top of the block are 0, 1, ...: the main rows start behind them
-        while main_row0 < len(prio) and prio[main_row0] == main_row0:
-            main_row0 += 1
-        tiles_y = -(-rows // TH)
-        assert all(p < main_row0 or p >= tiles_y - (len(prio) - main_row0) for p in prio), "edge rows must sit at the two ends"
         f = self.flags.ptr
-        return struct.pack("<7QI5i4i", up_rows, dn_rows, up_flag, dn_flag, f, f + 64, f + 128,
+        return struct.pack("<7QI4i4i4x", up_rows, dn_rows, up_flag, dn_flag, f, f + 64, f + 128,
                            (self.epoch + 1) & 0xFFFFFFFF, H, len(up_set) * tiles_x, len(dn_set) * tiles_x,
-                           len(prio), main_row0, *(prio + [0] * (4 - len(prio))))
+                           len(prio), *(prio + [0] * (4 - len(prio))))
 
 
 # ------------------------------------------------------------------------------ sharded storage
