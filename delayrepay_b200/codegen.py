@@ -20,6 +20,13 @@ from . import ranges
 
 with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "math_tables.cuh")) as _f:
     ERF2_ROWS = int([ln.split()[2] for ln in _f if ln.startswith("#define DR_ERF2_ROWS")][0])
+# third-generation erf (tools/gen_erf3.py): table uniform in sqrt(|x|/4), 11-12 instead of 14 issue
+# slots per element and half the ALU-pipe work.  Its source is appended ONLY to the staged kernels
+# that use it, so no other kernel's text (= cubin cache key) changes.
+with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "erf3.cuh")) as _f:
+    ERF3_SRC = _f.read()
+ERF3_ROWS = int([ln.split()[2] for ln in ERF3_SRC.splitlines() if ln.startswith("#define DR_ERF3_ROWS")][0])
+ERF3 = os.environ.get("DR_ERF_GEN", "3") == "3"
 
 CTYPE = {
     "?": "bool", "b": "signed char", "B": "unsigned char", "h": "short", "H": "unsigned short",
@@ -283,10 +290,13 @@ def gen_flat(name, prog, in_class, out_dts, vec_ok, stream, reduce=None, unroll=
         two_tier = two_tier or has_lane_fast(prog)
     safe_body = emit_body(prog, fast=False)
     fast_body = emit_body(prog, fast=True) if two_tier else safe_body
+    erf3 = ERF3 and erf_rep == 16
     if lockstep:
-        lock_body, lock_uniform = emit_body_lockstep(prog, in_class, V, sclasses, erf_rep)
+        lock_body, lock_uniform = emit_body_lockstep(prog, in_class, V, sclasses, erf_rep, erf3=erf3)
     src = []
     w = src.append
+    if erf3:
+        w(ERF3_SRC)
     if two_tier:
         fp = [f"const {ctype(a.dtype)} x{i}" for i, a in enumerate(arrays)]
         fp += [f"const {ctype(dt)} s{j}" for j, (_, dt) in enumerate(scalars)]
@@ -345,7 +355,7 @@ def gen_flat(name, prog, in_class, out_dts, vec_ok, stream, reduce=None, unroll=
         and os.environ.get("DR_PREFETCH", "0") != "0"
     ring_bytes = NS * VPL * len(c_inputs) * threads * 16 if staged else 0
     if meta is not None:
-        meta["smem"] = ring_bytes + (3 * ERF2_ROWS * 16 * 8 if erf_rep == 16 else 0)
+        meta["smem"] = ring_bytes + ((ERF3_ROWS * 16 * 20 if erf3 else 3 * ERF2_ROWS * 16 * 8) if erf_rep == 16 else 0)
         meta["threads"] = threads
     if staged:
         # operands arrive through PER-WARP shared-memory rings filled by 1-d TMA bulk copies: lane
@@ -359,7 +369,10 @@ def gen_flat(name, prog, in_class, out_dts, vec_ok, stream, reduce=None, unroll=
         TB = 512 * VPL                                   # bytes per operand per stage
         SB = nin * TB                                    # bytes per stage
         w("  extern __shared__ __align__(128) unsigned char dr_smem[];")
-        if erf_rep == 16:
+        if erf3:
+            w(f"  unsigned char* const dr_erf_tab = dr_smem + {ring_bytes};")
+            w("  dr_erf3_tab_stage(dr_erf_tab);")
+        elif erf_rep == 16:
             w(f"  float2* const dr_erf_tab = reinterpret_cast<float2*>(dr_smem + {ring_bytes});")
             w("  dr_erf2_tab_stage<16>(dr_erf_tab);")
         w(f"  __shared__ __align__(8) unsigned long long dr_bar[{WPB * NS}];")
@@ -573,7 +586,7 @@ def has_lane_fast(prog):
     return any(op in _LANE4_FAST and loop[0] == F32 for op, loop, _, _ in prog.instrs)
 
 
-def emit_body_lockstep(prog, in_class, V=4, sclasses=None, erf_rep=1):
+def emit_body_lockstep(prog, in_class, V=4, sclasses=None, erf_rep=1, erf3=False):
     """Lane-array form of the fused body: every SSA value is `T tK[4]` (or a plain scalar when
     it only depends on scalars / broadcast operands) and each instruction is applied to all
     four lanes at once -- packed f32x2 for float32 + - *, the dr_*4_fast lane functions for
@@ -632,10 +645,13 @@ def emit_body_lockstep(prog, in_class, V=4, sclasses=None, erf_rep=1):
         elif same and an is not None and op in _LANE4_R and k in an.check:
             flags = ", ".join(("true" if c else "false") if isinstance(c, bool) else str(int(c))
                               for c in an.check[k])
-            if op == "erf":
+            fn = _LANE4_R[op]
+            if op == "erf" and erf3:
+                fn = "dr_erf4_s"
+            elif op == "erf":
                 flags += f", {erf_rep}"
             extra = _TABLE_ARG.get(_LANE4_R[op], "")
-            lines.append(f"{_LANE4_R[op]}<{flags}>({', '.join(arr(r) for r in args)}, t{k}, bad{extra});")
+            lines.append(f"{fn}<{flags}>({', '.join(arr(r) for r in args)}, t{k}, bad{extra});")
         elif same and op in _LANE4_FAST and V == 4:
             extra = ", dr_erf_tab" if _LANE4_FAST[op] == "dr_erf4_tab" else ""
             lines.append(f"{_LANE4_FAST[op]}({', '.join(arr(r) for r in args)}, t{k}, bad{extra});")

@@ -320,6 +320,8 @@ def run_program(prog, outs, reduce=None, inplace=False):
         scl = ranges.scalar_classes(prog) if codegen.has_lane_fast(prog) else None
         key = ("flat", prog.key(), lay.in_class, tuple(d.str for d in out_dts), lay.vec_ok,
                stream_hint, red_key, inplace, scl)
+        if scl is not None and codegen.ERF3 and codegen.uses_erf_table(prog):
+            key += ("erf3",)               # the table generation is part of the kernel's identity
         gen_reduce = None if reduce is None else (reduce[0], reduce[1], reduce[2], None)
         meta = {}
         kern = get_kernel(key, lambda name: codegen.gen_flat(

@@ -222,6 +222,38 @@ def test_generation2_exp_log_erf_over_their_whole_domains(gpu):
         np.testing.assert_allclose(got, truth, rtol=0, atol=2e-6)
 
 
+def test_generation3_erf_in_staged_kernels(gpu):
+    """The staged (TMA-ring) kernels with a heavy body -- Black-Scholes' class -- use the third-
+    generation erf (tools/gen_erf3.py: table uniform in sqrt(|x|/4), indexed through MUFU.SQRT and
+    a magic-constant add).  `erf(x) / 1` makes such a kernel and returns erf(x) unchanged."""
+    from delayrepay_b200 import engine
+    rng = np.random.default_rng(55)
+    n = 1 << 20
+    with np.errstate(all="ignore"):
+        x = (np.exp(rng.uniform(-60, 2.5, n)) * rng.choice([-1.0, 1.0], n)).astype(np.float32)
+        x = np.concatenate([x, np.linspace(-6, 6, n // 2, dtype=np.float32),
+                            rng.uniform(-2.0 ** -7, 2.0 ** -7, n // 4).astype(np.float32),
+                            ((np.arange(0, 260, dtype=np.float64) / 256.0) ** 2 * 4).astype(np.float32),      # row centres
+                            (((np.arange(0, 260, dtype=np.float64) + 0.5) / 256.0) ** 2 * 4).astype(np.float32),  # row borders
+                            np.array([0.0, -0.0, 1e-45, -1e-45, 4.0, 3.9999998, 4.0000005, 1e30, -1e30, np.inf, -np.inf,
+                                      np.nan], np.float32)])
+        pad = (-x.size) % 4
+        x = np.concatenate([x, np.zeros(pad, np.float32)])
+        got = (erf(gpu.array(x)) / gpu.array(np.ones_like(x))).get()
+        assert "dr_erf4_s" in [k for k in engine._kernels.values() if k.name == engine.last_kernel_name()][0].source
+        want = erf(x)
+        assert np.array_equal(np.isnan(got), np.isnan(want))
+        ok = ~np.isnan(want)
+        worst = assert_close_to_numpy_or_truth(got[ok], want[ok], erf, (x[ok],), 2, "erf generation 3")
+        assert np.array_equal(np.signbit(got[ok]), np.signbit(want[ok])), "erf sign (incl. -0)"
+        truth = erf(x[ok].astype(np.float64))
+        ulp = np.abs(got[ok].astype(np.float64) - truth) / np.spacing(np.abs(truth).astype(np.float32)).astype(np.float64)
+        ulp[truth == 0] = 0
+        print(f"   erf generation 3: max {ulp.max():.3f} ulp from float64 (|x| >= 2^-9: "
+              f"{ulp[np.abs(x[ok]) >= 2.0 ** -9].max():.3f}), {worst} ulp from NumPy")
+        assert ulp.max() <= 1.5 and ulp[np.abs(x[ok]) >= 2.0 ** -9].max() <= 0.70
+
+
 def test_plan_cache_replays_are_exact(gpu):
     """engine._plans: a repeated expression structure launches a prepared plan (no planning);
     values, operand sharing patterns, layouts and scalar classes may change between replays."""
