@@ -20,9 +20,10 @@ from . import ranges
 
 with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "math_tables.cuh")) as _f:
     ERF2_ROWS = int([ln.split()[2] for ln in _f if ln.startswith("#define DR_ERF2_ROWS")][0])
-# third-generation erf (tools/gen_erf3.py): table uniform in sqrt(|x|/4), 11-12 instead of 14 issue
-# slots per element and half the ALU-pipe work.  Its source is appended ONLY to the staged kernels
-# that use it, so no other kernel's text (= cubin cache key) changes.
+# third-generation erf (tools/gen_erf3.py): table uniform in sqrt(|x|/4), ONE LDS.128 per evaluation
+# (4 shared-memory wavefronts instead of 6: the staged kernels are bound by the shared-memory pipe)
+# and 12 instead of 14 issue slots.  Its source is appended ONLY to the staged kernels that use it,
+# so no other kernel's text (= cubin cache key) changes.
 with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "erf3.cuh")) as _f:
     ERF3_SRC = _f.read()
 ERF3_ROWS = int([ln.split()[2] for ln in ERF3_SRC.splitlines() if ln.startswith("#define DR_ERF3_ROWS")][0])
@@ -355,7 +356,7 @@ def gen_flat(name, prog, in_class, out_dts, vec_ok, stream, reduce=None, unroll=
         and os.environ.get("DR_PREFETCH", "0") != "0"
     ring_bytes = NS * VPL * len(c_inputs) * threads * 16 if staged else 0
     if meta is not None:
-        meta["smem"] = ring_bytes + ((ERF3_ROWS * 16 * 20 if erf3 else 3 * ERF2_ROWS * 16 * 8) if erf_rep == 16 else 0)
+        meta["smem"] = ring_bytes + ((ERF3_ROWS * 8 * 16 if erf3 else 3 * ERF2_ROWS * 16 * 8) if erf_rep == 16 else 0)
         meta["threads"] = threads
     if staged:
         # operands arrive through PER-WARP shared-memory rings filled by 1-d TMA bulk copies: lane

@@ -1,38 +1,34 @@
-"""EXPERIMENT (round 2, measured, NOT shipped): a third-generation float32 erf for the staged
-Black-Scholes-class kernels (dr_erf4_s).  It was wired into codegen.gen_flat in commit 5139bfb,
-passed the parity suite on the B200 (max 1.433 ulp, 0.642 ulp for |x| >= 2^-9, Black-Scholes chain
-unchanged) and made NO difference to the kernel time -- 3.924 vs 3.892 ms over 20 steps and 4.50 vs
-4.48 ms over 200 on one box, 4.07 (640 threads) vs 4.12 ms on another: the box-to-box spread is
-larger than the effect (profiles/r2_bs_erf_generation3_experiment.txt).  Generation 2 stays.  The
-generator is kept because the table design and its error analysis are reusable.
+"""Third-generation float32 erf for the staged Black-Scholes-class kernels (dr_erf4_s).
 
-
-The second generation (tools/gen_math_v2.py: log-spaced accurate table, degree 4) spends 14 issue
-slots per element, six of them on the half-rate ALU pipe: two FMNMX clamps, a shift, an address
-merge, LEA, three LDS.64, FADD, four FFMA, a sign merge.  ncu (profiles/r2_bs_staged_kernel.txt):
-the kernel is issue-bound at 96 instructions per option with the ALU pipe its busiest (47 %).
-This generation moves the indexing off the ALU pipe and drops one load and one FFMA:
+WHY.  The Black-Scholes kernel is bound by the shared-memory pipe, not by instruction issue:
+an erf rewrite that removed 17 % of the ALU-pipe instructions but kept the table traffic changed
+nothing (3.92 vs 3.89 ms), while dropping ONE 4-byte table load per evaluation -- results wrong,
+timing only -- took 5.5 % off (4.00 -> 3.78 ms; profiles/r2_bs_erf_generation3_experiment.txt).
+Per option the kernel moves 21 shared-memory wavefronts: 3 for the operands, 2 for exp, 4 for
+log and 12 for the two erf look-ups (generation 2: three LDS.64 = 6 wavefronts each).  This
+generation makes an erf look-up ONE LDS.128 = 4 wavefronts, and cheaper to index:
 
     a' = sat(|x| / 4)                         FMUL.SAT: absolute value, scaling and the clamp at once
     s  = sqrt.approx(a')                      MUFU (the XU pipe is 19 % busy); only used for indexing
     t  = s + 49152                            FADD: ulp(t) = 2^-8, the low mantissa bits ARE round(256 s)
-    row address = (bits(t) << 8) + base       one LEA (the constant's bits are folded into base)
-    (c', C0, C1, C2) = LDS.128, C3 = LDS.32   16 bank-private replicas, conflict-free
+    row address = (bits(t) << 7) + base       one LEA (the constant's bits are folded into base)
+    (c', C0, C1, P) = LDS.128                 8 bank-private replicas (one per lane of a quarter warp)
+    C2 = P & 0xfffff800,  C3 = P << 21        C2 in the top 21 bits of one word, C3 in the low 11 (LOP3, SHL)
     d  = a' - c'                              exact (a'/c' in [0.56, 1.56])
-    erf|x| = C0 + d (C1 + d (C2 + d C3))      three FFMA (degree 3: the rows are narrow)
+    erf|x| = C0 + d (C1 + d (C2 + d C3))      three FFMA
 
-= 11 slots, two of them ALU.  Rows are uniform in s = sqrt(a'): 257 rows, row k centred at
-a' = (k/256)^2.  That spacing is the point: it is as fine as 2^-16 in x next to zero -- so rows 0
-and 1, which must use the odd series a'(C1 + a'^2 C3) (three roundings, <= 1.45 ulp), cover only
-|x| < 1.4e-4 (generation 2: |x| < 2.4e-4, 1.63 ulp) -- and about 1/64 in x where erf curves most.
-A table uniform in a' itself was tried first: its row 0 spans [0, 2^-7) and reaches 2.17 ulp.
-Row centres are accurate-table (Gal) points: c' near (k/256)^2 with erf(4 c') a float32 to
-< 2^-9 ulp, so C0 carries no rounding error.  Measured against float64 / mpmath on 3.4 M points:
-0.51-0.64 ulp for |x| >= 2^-9, 0.82 / 1.11 / 1.43 ulp in the three binades below (bar: 2 ulp).
-The approximate square root only selects the row: a row is fitted 10 % beyond its interval, and
-perturbing s by +-3 ulp changes no result bound.
+Rows are uniform in s = sqrt(a'): 257 rows, row k centred at a' = (k/256)^2.  That spacing is as
+fine as 2^-16 in x next to zero -- so rows 0 and 1, which must use the odd series a'(C1 + a'^2 C3)
+(three roundings), cover only |x| < 1.4e-4 (generation 2: |x| < 2.4e-4) -- and about 1/64 in x where
+erf curves most, which makes d so small that C2 needs 13 significant bits and C3 three: they share
+one word (C1 is refitted after the quantisation and absorbs its linear part).  A table uniform in a' itself was tried first:
+its row 0 spans [0, 2^-7) and reaches 2.17 ulp.  Row centres are accurate-table (Gal) points: c'
+near (k/256)^2 with erf(4 c') a float32 to < 2^-9 ulp, so C0 carries no rounding error.  The
+approximate square root only selects the row: a row is fitted 10 % beyond its interval, and
+perturbing s by +-3 ulp changes no result bound.  Table: 257 x 8 x 16 B = 32.1 KiB (generation 2:
+84 KiB).
 
-  python tools/gen_erf3.py            # accuracy report (NumPy float32 emulation)
+  python tools/gen_erf3.py            # accuracy report (NumPy float32 emulation vs float64)
   python tools/gen_erf3.py --emit     # write delayrepay_b200/csrc/erf3.cuh
 """
 import os
@@ -51,6 +47,22 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 def fma(a, b, c):
     return (np.float64(a) * np.float64(b) + np.float64(c)).astype(f32)
+
+
+C2_BITS = 21            # the packed word: C2 = its top 21 bits (13 significant), C3 = the low 11 bits
+C3_BITS = 32 - C2_BITS  # (sign, 8 exponent bits, 2 mantissa bits), shifted up by 21
+
+
+def trunc_bits(v, bits):
+    """float32 value(s) rounded to nearest-even on their top `bits` bits, returned as float32."""
+    drop = 32 - bits
+    b = np.asarray(v, f32).view(np.uint32).astype(np.uint64)
+    b = (b + ((1 << (drop - 1)) - 1) + ((b >> drop) & 1)) & ((0xFFFFFFFF >> drop) << drop)
+    return b.astype(np.uint32).view(f32)
+
+
+def bf16(v):
+    return trunc_bits(v, C3_BITS)
 
 
 def gal_centre(k, search=6000):
@@ -74,7 +86,7 @@ def table():
     worst = 0.0
     for k in range(ROWS):
         if k <= 1:           # |x| < 1.4e-4: erf(4a') = a' (8/sqrt(pi) - 128/(3 sqrt(pi)) a'^2), c' = C0 = 0
-            rows[k] = [0, 0, f32(4 * two), 0, f32(-64 * two / 3)]
+            rows[k] = [0, 0, f32(4 * two), 0, bf16(f32(-64 * two / 3))]
             continue
         if k == ROWS - 1:    # a' = 1 (|x| >= 4 after the clamp): erf = 1 in float32, d = 0
             rows[k] = [1, 1, 0, 0, 0]
@@ -88,9 +100,15 @@ def table():
         y = np.array([float(mp.erf(mp.mpf(v) * 4) - mp.mpf(float(c0))) for v in x])
         m = np.abs(d) > 1e-15
         wgt = 1 / np.abs(y[m] + float(c0))                      # relative error of the result
-        A = np.stack([d[m], d[m] ** 2, d[m] ** 3], 1)
-        sol = np.linalg.lstsq(A * wgt[:, None], y[m] * wgt, rcond=None)[0]
-        rows[k] = [c, c0, f32(sol[0]), f32(sol[1]), f32(sol[2])]
+        dm, ym = d[m], y[m]
+        A = np.stack([dm, dm ** 2, dm ** 3], 1)
+        sol = np.linalg.lstsq(A * wgt[:, None], ym * wgt, rcond=None)[0]
+        # C3 and C2 travel as bf16: quantise the highest first and refit what is below it
+        c3 = float(bf16(f32(sol[2])))
+        sol2 = np.linalg.lstsq(A[:, :2] * wgt[:, None], (ym - c3 * dm ** 3) * wgt, rcond=None)[0]
+        c2 = float(trunc_bits(f32(sol2[1]), C2_BITS))
+        c1 = np.linalg.lstsq(A[:, :1] * wgt[:, None], (ym - c3 * dm ** 3 - c2 * dm ** 2) * wgt, rcond=None)[0][0]
+        rows[k] = [c, c0, f32(c1), f32(c2), f32(c3)]
     return rows, worst
 
 
@@ -131,25 +149,28 @@ def report(T):
 
 
 def emit(T, path):
-    flat = ", ".join(f"{float(v)!r}f" for v in T.ravel())
+    words = np.zeros((ROWS, 4), dtype=np.uint32)
+    words[:, 0:3] = T[:, 0:3].view(np.uint32)
+    c2b, c3b = T[:, 3].view(np.uint32), T[:, 4].view(np.uint32)
+    assert not (c2b & ((1 << C3_BITS) - 1)).any() and not (c3b & ((1 << C2_BITS) - 1)).any(), "C2 / C3 not quantised"
+    words[:, 3] = c2b | (c3b >> C2_BITS)
+    flat = ", ".join(f"0x{int(v):08x}u" for v in words.ravel())
     text = f"""// GENERATED by tools/gen_erf3.py -- do not edit.
-// Third-generation float32 erf (accurate table uniform in sqrt(|x|/4), degree 3): the generator's
-// docstring has the design and the measured error.  Appended only to the kernels that use it
-// (codegen.gen_flat: staged kernels with the bank-private table), so every other kernel's text --
-// and cubin cache entry -- is unchanged.
+// Third-generation float32 erf (accurate table uniform in sqrt(|x|/4), degree 3, one LDS.128 per
+// evaluation): the generator's docstring has the design and the measured error.  Appended only to
+// the kernels that use it (codegen.gen_flat: staged kernels with the bank-private table), so
+// every other kernel's text -- and cubin cache entry -- is unchanged.
 #define DR_ERF3_ROWS {ROWS}
-__constant__ float DR_ERF3_TAB[{ROWS * 5}] = {{ {flat} }};
-// shared-memory layout: float4 main[row * 16 + replica] = (c', C0, C1, C2), then
-// float c3[row * 16 + replica]; replica = lane & 15, so the 8 lanes of an LDS.128 wavefront and
-// the lanes of an LDS.32 never meet in a bank.
-#define DR_ERF3_SMEM_BYTES ({ROWS} * 16 * 20)
+// row = (c', C0, C1, [C2: top {C2_BITS} bits | C3: {C3_BITS} bits]) as raw words
+__constant__ unsigned DR_ERF3_TAB[{ROWS * 4}] = {{ {flat} }};
+// shared-memory layout: uint4 tab[row * 8 + replica], replica = lane & 7: the 8 lanes of an
+// LDS.128 wavefront (a quarter warp) read 8 different 16-byte bank groups, whatever their rows.
+#define DR_ERF3_SMEM_BYTES ({ROWS} * 8 * 16)
 __device__ __forceinline__ void dr_erf3_tab_stage(unsigned char* smem) {{
-  float4* main4 = reinterpret_cast<float4*>(smem);
-  float* c3 = reinterpret_cast<float*>(smem + {ROWS} * 16 * 16);
-  for (int i = threadIdx.x; i < {ROWS} * 16; i += blockDim.x) {{
-    const int r = (i >> 4) * 5;
-    main4[i] = make_float4(DR_ERF3_TAB[r], DR_ERF3_TAB[r + 1], DR_ERF3_TAB[r + 2], DR_ERF3_TAB[r + 3]);
-    c3[i] = DR_ERF3_TAB[r + 4];
+  uint4* tab = reinterpret_cast<uint4*>(smem);
+  for (int i = threadIdx.x; i < {ROWS} * 8; i += blockDim.x) {{
+    const int r = (i >> 3) * 4;
+    tab[i] = make_uint4(DR_ERF3_TAB[r], DR_ERF3_TAB[r + 1], DR_ERF3_TAB[r + 2], DR_ERF3_TAB[r + 3]);
   }}
   __syncthreads();
 }}
@@ -159,9 +180,7 @@ template <bool CHECK>
 __device__ __forceinline__ void dr_erf4_s(const f4& x, f4& o, bool& bad, const unsigned char* smem) {{
   bool ok = true;
   // this lane's replica of row 0, minus the magic constant's bits scaled like the row index
-  const unsigned lane16 = (threadIdx.x & 15u) * 16u;
-  const unsigned base4 = dr_smem_addr(smem) + lane16 - (0x47400000u << 8);
-  const unsigned base1 = dr_smem_addr(smem) + {ROWS} * 16 * 16 + (lane16 >> 2) - (0x47400000u << 6);
+  const unsigned base = dr_smem_addr(smem) + (threadIdx.x & 7u) * 16u - (0x47400000u << 7);
 #pragma unroll
   for (int l = 0; l < 4; ++l) {{
     if (CHECK) ok = ok && (x[l] == x[l]);
@@ -169,14 +188,14 @@ __device__ __forceinline__ void dr_erf4_s(const f4& x, f4& o, bool& bad, const u
     float s;
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(ap));
     const unsigned tb = __float_as_uint(__fadd_rn(s, 49152.0f));
-    float4 r;
-    float c3;
-    asm("ld.shared.v4.f32 {{%0, %1, %2, %3}}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(base4 + (tb << 8)));
-    asm("ld.shared.f32 %0, [%1];" : "=f"(c3) : "r"(base1 + (tb << 6)));
-    const float d = __fsub_rn(ap, r.x);
-    float p = fmaf(c3, d, r.w);
-    p = fmaf(p, d, r.z);
-    p = fmaf(p, d, r.y);
+    float c, c0, c1;
+    unsigned pk;
+    asm("ld.shared.v4.b32 {{%0, %1, %2, %3}}, [%4];" : "=f"(c), "=f"(c0), "=f"(c1), "=r"(pk) : "r"(base + (tb << 7)));
+    const float c2 = __uint_as_float(pk & {hex(((0xFFFFFFFF >> C3_BITS) << C3_BITS))}u), c3 = __uint_as_float(pk << {C2_BITS});
+    const float d = __fsub_rn(ap, c);
+    float p = fmaf(c3, d, c2);
+    p = fmaf(p, d, c1);
+    p = fmaf(p, d, c0);
     o[l] = __int_as_float(__float_as_int(p) | (__float_as_int(x[l]) & 0x80000000));
   }}
   if (CHECK) bad = bad || !ok;
