@@ -291,7 +291,10 @@ def gen_flat(name, prog, in_class, out_dts, vec_ok, stream, reduce=None, unroll=
         two_tier = two_tier or has_lane_fast(prog)
     safe_body = emit_body(prog, fast=False)
     fast_body = emit_body(prog, fast=True) if two_tier else safe_body
-    erf3 = ERF3 and erf_rep == 16
+    # generation 3 of erf wherever a flat lockstep kernel uses the table: carved out of dynamic
+    # shared memory behind the operand rings when staged, a static 32 KiB array otherwise
+    erf3 = ERF3 and (erf_rep == 16 or (lockstep and GEN2 and V == 4 and uses_erf_table(prog)
+                                       and os.environ.get("DR_ERF3_UNSTAGED", "1") != "0"))
     if lockstep:
         lock_body, lock_uniform = emit_body_lockstep(prog, in_class, V, sclasses, erf_rep, erf3=erf3)
     src = []
@@ -327,6 +330,9 @@ def gen_flat(name, prog, in_class, out_dts, vec_ok, stream, reduce=None, unroll=
     if lockstep and uses_erf_table(prog):
         if GEN2 and erf_rep == 16:
             pass            # carved out of dynamic shared memory behind the operand rings (below)
+        elif erf3:
+            w("  __shared__ __align__(16) unsigned char dr_erf_tab[DR_ERF3_SMEM_BYTES];")
+            w("  dr_erf3_tab_stage(dr_erf_tab);")
         elif GEN2:
             w("  __shared__ float2 dr_erf_tab[3 * DR_ERF2_ROWS];")
             w("  dr_erf2_tab_stage<1>(dr_erf_tab);")
@@ -370,7 +376,7 @@ def gen_flat(name, prog, in_class, out_dts, vec_ok, stream, reduce=None, unroll=
         TB = 512 * VPL                                   # bytes per operand per stage
         SB = nin * TB                                    # bytes per stage
         w("  extern __shared__ __align__(128) unsigned char dr_smem[];")
-        if erf3:
+        if erf3 and erf_rep == 16:
             w(f"  unsigned char* const dr_erf_tab = dr_smem + {ring_bytes};")
             w("  dr_erf3_tab_stage(dr_erf_tab);")
         elif erf_rep == 16:
