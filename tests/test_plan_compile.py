@@ -103,7 +103,7 @@ def test_all_workloads_generate_and_compile(dry):
     body = kern.source[kern.source.index('extern "C" __global__'):]
     # staged per-warp TMA rings + lockstep body with the guards the interval analysis left
     assert "dr_bulk_load_s(" in body and "dr_elect()" in body and "__syncthreads();          //" not in body
-    assert body.count("dr_div4_r<false, false>(") == 2 and "dr_erf4_gal<false, 16>(" in body
+    assert body.count("dr_div4_r<false, false>(") == 2 and "dr_erf4_s<false>(" in body      # generation-3 erf
     assert "dr_log4_t<false>(" in body and "dr_sqrt4_r<false>(" in body and "dr_exp4_t<2>(" in body
     assert "dr_rg.pos4(v0[u].v); dr_rg.pos4(v1[u].v); dr_rg.pos4(v2[u].v);" in body
     i = wl.make_inputs("l2", 4096)
