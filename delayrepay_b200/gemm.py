@@ -203,3 +203,112 @@ def matmul_tf32x3(a_node, b_node):
         kern.meta["smem_set"] = True
     launch(kern, dev, (-(-n // BN), -(-m // BM), 1), 192, a, smem=SMEM_BYTES)
     return out
+
+
+# --------------------------------------------------------------------------- generic tiled GEMM
+# float64 and integer A @ B have no tcgen05 path (the tensor cores take TF32 / bf16 / fp8 here).
+# Round 1 sent them to the `cols` reduction kernel: one thread per output element, no reuse --
+# 16384 x 16384 @ 16384 x 64 float64 took 20.4 ms (105 GB/s, profiles/r1_surface_ops_after.txt).
+# This is the classic shared-memory / register-tiled kernel: a 64 x 64 output tile per CTA of 256
+# threads, BK = 16 deep slices of A and B staged in shared memory (A transposed on the way in, so
+# both are read conflict-free), a 4 x 4 accumulator tile per thread.  Accumulation is in the result
+# type, one term at a time in k order (float64: same order as the reference's BLAS is not defined;
+# the parity bar is rtol 1e-12 of the terms' scale; integers: exact, wrap-around like NumPy).
+_TILED_SRC = r"""
+extern "C" __global__ void __launch_bounds__(256) NAME(const T* __restrict__ A, const T* __restrict__ B,
+    T* __restrict__ Cout, int M, int N, int K, i64 lda, i64 ldb, i64 ldc) {
+  __shared__ T As[16][64 + PAD];          // As[k][m]
+  __shared__ T Bs[16][64 + PAD];          // Bs[k][n]
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  ACC acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = (ACC)0;
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    // A tile 64 x 16: thread -> (row = tid / 4 ... ), 4 elements each; coalesced along k
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int e = tid + r * 256, mm = e >> 4, kk = e & 15;
+      const int gm = m0 + mm, gk = k0 + kk;
+      As[kk][mm] = (gm < M && gk < K) ? A[(i64)gm * lda + gk] : (T)0;
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int e = tid + r * 256, kk = e >> 6, nn = e & 63;
+      const int gk = k0 + kk, gn = n0 + nn;
+      Bs[kk][nn] = (gk < K && gn < N) ? B[(i64)gk * ldb + gn] : (T)0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      ACC a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = (ACC)As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = (ACC)Bs[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = MAC(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int gm = m0 + ty * 4 + i;
+    if (gm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gn = n0 + tx * 4 + j;
+      if (gn < N) Cout[(i64)gm * ldc + gn] = (T)acc[i][j];
+    }
+  }
+}
+"""
+
+
+def matmul_tiled(a_node, b_node, res_dt):
+    """A(M,K) @ B(K,N) in `res_dt` (float64 / float32 without a tensor path / integers) on the
+    register-tiled kernel.  Operands are materialised contiguously in the result type first (their
+    elementwise producers are fused into that pass)."""
+    from .delayarray import as_dtype
+    from .codegen import ctype
+    res_dt = np.dtype(res_dt)
+    a_dev = as_dtype(a_node, res_dt)._force()
+    b_dev = as_dtype(b_node, res_dt)._force()
+    if not a_dev.is_contiguous:
+        a_dev = a_dev.copy()
+    if not b_dev.is_contiguous:
+        b_dev = b_dev.copy()
+    m, k = a_dev.shape
+    n = b_dev.shape[1]
+    dev = a_dev.dev
+    out = DeviceArray.empty((m, n), res_dt, dev if dev >= 0 else None)
+    T = ctype(res_dt)
+    if res_dt.kind == "f":
+        acc, mac = T, "fma"
+    elif res_dt.kind == "b":
+        raise TypeError("boolean matmul is not supported")
+    else:
+        # signed overflow is undefined in C++ (and NVRTC uses that): accumulate unsigned, like the
+        # elementwise integer path
+        acc = {1: "unsigned char", 2: "unsigned short", 4: "unsigned int", 8: "unsigned long long"}[res_dt.itemsize]
+        mac = "DR_IMAC"
+    src = ("#define DR_IMAC(a, b, c) ((a) * (b) + (c))\n" if mac == "DR_IMAC" else "") + \
+        _TILED_SRC.replace("NAME", "KNAME").replace("ACC", acc).replace("MAC", mac) \
+        .replace("PAD", "4" if res_dt.itemsize == 4 else "2").replace(" T ", f" {T} ") \
+        .replace("const T*", f"const {T}*").replace("(T)", f"({T})").replace("T* __restrict__ Cout", f"{T}* __restrict__ Cout")
+    kern = get_kernel(("gemm_tiled", res_dt.str), lambda name: src.replace("KNAME", name))
+    a = Args()
+    a.ptr(a_dev.ptr)
+    a.ptr(b_dev.ptr)
+    a.ptr(out.ptr)
+    for v in (m, n, k):
+        a.scalar(v, np.int32)
+    a.i64(k)
+    a.i64(n)
+    a.i64(n)
+    launch(kern, dev, (-(-n // 64), -(-m // 64), 1), 256, a)
+    return out

@@ -222,6 +222,30 @@ def test_generation2_exp_log_erf_over_their_whole_domains(gpu):
         np.testing.assert_allclose(got, truth, rtol=0, atol=2e-6)
 
 
+@pytest.mark.parametrize("shape", [(300, 200, 150), (64, 1000, 64), (1025, 33, 129), (2048, 512, 64)])
+def test_tiled_gemm_float64_and_integers(gpu, shape):
+    """float64 / integer A @ B (no tensor-core path): the register-tiled kernel (gemm.matmul_tiled).
+    float64 within rtol 1e-12 of the terms' scale, integers exact including wrap-around."""
+    from delayrepay_b200 import engine
+    m, k, n = shape
+    rng = np.random.default_rng(m + k + n)
+    a, b = rng.standard_normal((m, k)), rng.standard_normal((k, n))
+    got = (gpu.array(a) @ gpu.array(b)).get()
+    assert engine.last_kernel_name().startswith("dr_gemm_tiled_")
+    scale = np.abs(a) @ np.abs(b)
+    assert np.max(np.abs(got - a @ b) / scale) <= 1e-12
+    # fused producers and a transposed (strided) operand
+    got = ((gpu.array(a) * 2 + 1) @ gpu.array(b.T.copy()).T).get()
+    assert np.max(np.abs(got - (a * 2 + 1) @ b) / (np.abs(a * 2 + 1) @ np.abs(b))) <= 1e-12
+    for dt in (np.int32, np.int64, np.uint8):
+        info = np.iinfo(dt)
+        ia = rng.integers(info.min // 2 if dt is not np.uint8 else 0, info.max // 2, (m, k)).astype(dt)
+        ib = rng.integers(0, 7, (k, n)).astype(dt)
+        with np.errstate(over="ignore"):
+            want = ia @ ib                                  # wraps
+        assert_bits_equal((gpu.array(ia) @ gpu.array(ib)).get(), want, f"{np.dtype(dt).name} matmul")
+
+
 def test_generation3_erf_in_staged_kernels(gpu):
     """The staged (TMA-ring) kernels with a heavy body -- Black-Scholes' class -- use the third-
     generation erf (tools/gen_erf3.py: table uniform in sqrt(|x|/4), indexed through MUFU.SQRT and
