@@ -865,6 +865,9 @@ def _run_matmul(node):
     res_dt = node.dtype
     from .delayarray import as_dtype
     pa = planner.build_program([as_dtype(a, res_dt)])
+    skinny = _try_mm_skinny(node, pa, m, k, n, res_dt)      # first: it needs nothing of what follows
+    if skinny is not None:
+        return skinny
     pb = planner.build_program([as_dtype(b, res_dt)])
     prog = planner.Program()
     triples = []
@@ -887,9 +890,6 @@ def _run_matmul(node):
         for buf in p.leaf_bufs:
             if all(buf is not x for x in prog.leaf_bufs):
                 prog.leaf_bufs.append(buf)
-    skinny = _try_mm_skinny(node, pa, m, k, n, res_dt)
-    if skinny is not None:
-        return skinny
     if res_dt == np.float32 and min(m, n) >= 8 and max(m, n) >= 128 and k >= 64 \
             and not os.environ.get("DR_NO_TCGEN05"):
         from . import gemm
