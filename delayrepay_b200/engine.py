@@ -895,7 +895,7 @@ def _run_matmul(node):
         from . import gemm
         node._stamp = _stamp_of(pa) + _stamp_of(pb)
         return gemm.matmul_tf32x3(a, b)
-    if res_dt.kind in "fiu" and m * n >= 4096 and k >= 32 and m * n * k >= (1 << 22) \
+    if res_dt.kind in "fiu" and m * n >= 4096 and k >= 32 and m * n * k >= (1 << 21) \
             and not os.environ.get("DR_NO_TILED_GEMM"):
         # float64 / integer (and float32 shapes without a tensor path): register-tiled kernel
         from . import gemm
