@@ -1043,14 +1043,15 @@ __device__ __forceinline__ unsigned long long dr_globaltimer() {
   return t;
 }
 // Spin until *flag has reached step `want` (wrap-safe).  A neighbour that never signals (its
-// process died) must not hang the GPU: trap after 20 s.
+// process died) must not hang the GPU: trap after 120 s (a rank that is
+// merely late -- a cold NVRTC compile, a paged-out interpreter -- is waited for).
 __device__ __forceinline__ void dr_wait_epoch(const unsigned* flag, unsigned want) {
   unsigned long long t0 = 0;
   while ((int)(dr_ld_acquire_sys(flag) - want) < 0) {
     __nanosleep(100);
     const unsigned long long now = dr_globaltimer();
     if (t0 == 0) t0 = now;
-    else if (now - t0 > 20000000000ull) __trap();
+    else if (now - t0 > 120000000000ull) __trap();
   }
   // the halo rows were written by another GPU (generic proxy); the TMA unit reads them through
   // the async proxy

@@ -251,6 +251,7 @@ def init(devices=None, rank=None, world=None, local_rank=None):
     Otherwise SPMD from RANK / WORLD_SIZE / LOCAL_RANK (torchrun); world 1 = a trivial mesh."""
     if _state["mesh"] is not None and devices is None and rank is None:
         return _state["mesh"]
+    shutdown()                                   # a new mesh replaces the old one (its communicators are destroyed)
     from . import engine
     dry = engine.is_dry()
     if devices is not None:
@@ -1201,8 +1202,7 @@ def from_local(block, halo=0, mesh=None):
         at += c
     first = devs[mesh.local[0]]
     if halo:
-        return from_global_fn(lambda r0, r1: (_ for _ in ()).throw(NotImplementedError(
-            "from_local with a halo: use shard() / from_global_fn()")), (at,) + first.shape[1:], first.dtype)
+        raise NotImplementedError("from_local with a halo: use shard() / from_global_fn(), which fill the halo rows")
     base = ShardedBase.__new__(ShardedBase)
     base.mesh, base.gshape, base.dtype = mesh, (at,) + tuple(first.shape[1:]), first.dtype
     base.bounds, base.H, base.links = bounds, 0, {}
