@@ -311,6 +311,7 @@ class HaloLink:
         self.base = weakref.ref(base)
         self.rank, self.H = rank, base.H
         self.epoch = 0
+        self.waited = 0                   # last step whose pushed halo rows a wait kernel has covered
         self.dirty = False                # halo rows stale: something else wrote the array
         self._partner = None
         self.flags = None                 # DeviceBuffer (peer): my flags + counters
@@ -492,6 +493,7 @@ class ShardedBase:
         mesh.barrier()
         for l in self.links.values():
             l.dirty = False
+            l.waited = l.epoch
 
 
 # ------------------------------------------------------------------------------ the backend array
@@ -772,15 +774,61 @@ def _replicate(view):
 _halo_reads = set()        # bases whose halo rows were addressed since the last _refresh_halos()
 
 
-def _refresh_halos(bases=None):
-    """Peer-copy exchange for every base whose halo rows are about to be read and are stale.
-    Collective: every rank reaches this point with the same set (same program, same state)."""
+_WAIT_SRC = r"""
+// One thread: spin until both neighbours have published stencil step `epoch` (or there is no
+// neighbour on that side: null pointer).  Launched in front of a kernel that reads halo rows which
+// the neighbours' stencil kernels wrote, when that kernel is not the halo stencil itself (which
+// performs the same acquire inside).
+extern "C" __global__ void NAME(const unsigned* flag_up, const unsigned* flag_dn, unsigned epoch) {
+  const unsigned* f[2] = {flag_up, flag_dn};
+  for (int s = 0; s < 2; ++s) {
+    if (f[s] == nullptr) continue;
+    unsigned long long t0 = 0;
+    for (;;) {
+      unsigned v;
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f[s]) : "memory");
+      if ((int)(v - epoch) >= 0) break;
+      __nanosleep(100);
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now; else if (now - t0 > 120000000000ull) __trap();
+    }
+  }
+}
+"""
+
+
+def _wait_for_pushed_halos(base):
+    """The halo rows of `base` were written by the neighbours' stencil kernels (no host sync): a
+    consumer other than the next halo stencil of the same array must not start before their
+    flags say so.  One 1-thread kernel per local block, once per stencil step."""
+    from . import engine
+    for r, link in base.links.items():
+        if link.epoch == link.waited or (link.up is None and link.dn is None):
+            continue
+        blk = base.blocks[r]
+        kern = engine.get_kernel(("halo_wait",), lambda name: _WAIT_SRC.replace("NAME", name))
+        a = engine.Args()
+        a.ptr(link.flags.ptr if link.up else 0)
+        a.ptr(link.flags.ptr + 64 if link.dn else 0)
+        a.scalar(link.epoch & 0xFFFFFFFF, np.uint32)
+        engine.launch(kern, blk.dev, 1, 1, a)
+        link.waited = link.epoch
+
+
+def _refresh_halos(bases=None, stencil_target=None):
+    """Before halo rows are read: the peer-copy exchange for every base whose halo copies are stale
+    (collective: every rank reaches this point with the same set -- same program, same state),
+    and a device-side wait for halo rows that were pushed by the neighbours' stencil kernels --
+    except for `stencil_target`, whose own halo stencil performs that wait itself."""
     todo = list(_halo_reads if bases is None else bases)
     if bases is None:
         _halo_reads.clear()
     for b in todo:
         if b.halo_dirty:
             b.exchange_halos()
+        elif b is not stencil_target and b.links:
+            _wait_for_pushed_halos(b)
     return todo
 
 
@@ -1060,7 +1108,7 @@ def assign(target, value, drop_row_axis=False):
         key = (node._psig, target.layout_key(), _scalar_sig(node._pops))
         plan = _assign_plans.get(key)
         if plan is not None:
-            _refresh_halos(plan[1])
+            _refresh_halos(plan[1], stencil_target=plan[3])
             _write(base, plan[0])
             plan[2][0] = node             # keeps the global right-hand side hash-consed
             return
@@ -1089,12 +1137,16 @@ def assign(target, value, drop_row_axis=False):
                 loc = _on_device(mesh, arr, mesh.devs[r])
                 vloc = da.NPArray(loc[i0:i1] if full else loc)
         todo.append((tloc, vloc))
+    # a self-stencil on an array with links runs as the halo kernel, which waits for the pushed rows
+    # itself; the first time (no plan yet) an extra wait kernel is harmless
     reads = _refresh_halos()
+    before = {r: l.epoch for r, l in base.links.items()}
     _write(base, todo)
+    stepped = bool(base.links) and all(l.epoch != before[r] for r, l in base.links.items())
     if key is not None:
         if len(_assign_plans) > 256:
             _assign_plans.clear()
-        _assign_plans[key] = (todo, reads, [node])
+        _assign_plans[key] = (todo, reads, [node], base if stepped else None)
 
 
 def _write(base, todo):

@@ -76,6 +76,32 @@ def test_sharded_heat_with_boundary_writes_and_fallback_exchange(gpu, mesh3):
     assert_bits_equal(u.get(), want.get(), "heat with boundary writes")
 
 
+def test_other_consumers_of_pushed_halo_rows(gpu, mesh3):
+    """Halo rows pushed by the neighbours' stencil kernels are also read by kernels that are not
+    the halo stencil (a difference of shifted views, a reduction over them, a stencil into ANOTHER
+    array): those are preceded by a device-side wait on the neighbours' flags."""
+    from delayrepay_b200 import engine
+    dr = gpu
+    rng = np.random.default_rng(21)
+    h = rng.random((300, 256), dtype=np.float32)
+    u, want = dr.shard(h), h.copy()
+    v = dr.shard(np.zeros_like(h))
+    for _ in range(4):
+        wl.heat(dr, u, 3)
+        for _ in range(3):
+            want[1:-1, 1:-1] = want[1:-1, 1:-1] + np.float32(0.1) * (
+                want[2:, 1:-1] + want[:-2, 1:-1] + want[1:-1, 2:] + want[1:-1, :-2] - np.float32(4.0) * want[1:-1, 1:-1])
+        l0 = engine.stats["launches"]
+        grad = u[2:, 1:-1] - u[:-2, 1:-1]                    # reads one row into each halo
+        assert_bits_equal(grad.get(), want[2:, 1:-1] - want[:-2, 1:-1], "vertical difference")
+        assert engine.stats["launches"] - l0 >= 3 + 2, "a wait kernel per block with a neighbour"
+        got = float(np.sum(np.abs(u[2:, :] - u[:-2, :])))
+        ref = float(np.sum(np.abs(want[2:, :] - want[:-2, :]).astype(np.float64)))
+        assert abs(got - ref) <= 1e-5 * ref
+        v[1:-1, :] = u[2:, :] + u[:-2, :]
+        assert_bits_equal(v.get()[1:-1], want[2:, :] + want[:-2, :], "stencil into another array")
+
+
 def test_sharded_heat_not_stencil_eligible_shape(gpu, mesh3):
     """203 columns (not a multiple of the vector width): the blocks take the generic
     temporary + copy path and the explicit exchange every step -- slow, but exact."""
@@ -276,6 +302,9 @@ wl.heat(dr, u, 60)
 assert engine.stats["launches"] - l0 == 60
 want = refcpu.leaf(h.copy()); wl.heat(refcpu, want, 60)
 assert u.get().tobytes() == want.get().tobytes(), "sharded heat differs"
+g = (u[2:, 1:-1] - u[:-2, 1:-1]).get()                     # non-stencil consumer of pushed halo rows
+wn = want.get()
+assert g.tobytes() == (wn[2:, 1:-1] - wn[:-2, 1:-1]).tobytes(), "difference of shifted views differs"
 u[0, :] = 1.0; want[0, :] = 1.0
 wl.heat(dr, u, 3); wl.heat(refcpu, want, 3)
 assert u.get().tobytes() == want.get().tobytes(), "sharded heat after a boundary write differs"
