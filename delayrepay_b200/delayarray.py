@@ -90,7 +90,9 @@ class Memoiser(type):
                 hit = None
         elif hit is not None:
             arr = hit.__dict__.get("array")
-            if arr is not None and (not _stamp_valid(hit._stamp) or arr.buf.version != 0):
+            if arr is not None and (hit.__dict__.get("_mesh") is not None or getattr(arr, "_is_shard_view", False)):
+                hit = None          # sharded results carry no buffer stamps: a fresh capture recomputes
+            elif arr is not None and (not _stamp_valid(hit._stamp) or arr.buf.version != 0):
                 # evaluated before one of its inputs was written: that node keeps ITS value
                 # (whoever holds it sees a snapshot, as with NumPy); this new capture must see the
                 # new data.  Likewise a node whose OWN result storage was written afterwards
