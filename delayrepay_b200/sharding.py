@@ -273,15 +273,16 @@ def init(devices=None, rank=None, world=None, local_rank=None):
             dev = -1
         rdv, comms = None, {}
         if world > 1:
-            _lib.init()
             rdv = Rendezvous(rank, world)
-            uid = (C.c_uint8 * 128)()
-            if rank == 0:
-                check(lib.drc_nccl_get_unique_id(uid))
-            raw = rdv.bcast(bytes(uid))
-            comm = C.c_uint64()
-            check(lib.drc_nccl_init_rank(dev, world, rank, (C.c_uint8 * 128).from_buffer_copy(raw), C.byref(comm)))
-            comms = {rank: comm.value}
+            if not dry:            # (dry run: the ranks still meet and exchange metadata, nothing touches a GPU)
+                _lib.init()
+                uid = (C.c_uint8 * 128)()
+                if rank == 0:
+                    check(lib.drc_nccl_get_unique_id(uid))
+                raw = rdv.bcast(bytes(uid))
+                comm = C.c_uint64()
+                check(lib.drc_nccl_init_rank(dev, world, rank, (C.c_uint8 * 128).from_buffer_copy(raw), C.byref(comm)))
+                comms = {rank: comm.value}
         mesh = Mesh(world, [rank], {rank: dev}, rdv, comms)
     _state["mesh"] = mesh
     return mesh

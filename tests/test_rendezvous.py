@@ -86,3 +86,54 @@ def test_sharded_expressions_plan_and_compile_without_a_gpu():
                 (u[3:] + u[:-3]).run()          # needs rows 3 away, the blocks hold 1
         finally:
             sharding.shutdown()
+
+
+def _spmd_dry_worker(rank, world, port, q):
+    """One rank of an SPMD run in dry mode: everything but the kernels -- rendezvous, partition,
+    neighbour wiring, localisation, planning and NVRTC compilation of the halo stencil."""
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    sys.path.insert(0, ROOT)
+    import numpy as np
+    import delayrepay_b200 as dr
+    from delayrepay_b200 import engine, sharding
+    import workloads as wl
+    with engine.dry_run() as log:
+        mesh = sharding.init()
+        assert mesh.spmd and mesh.world == world and mesh.local == [rank]
+        h = wl.make_inputs("heat", 516)["u"][:515]          # 515 x 516: uneven row split, vectorisable columns
+        u = dr.shard(h)
+        base = u.array.base
+        link = base.links[rank]
+        n0 = len(log)
+        wl.heat(dr, u, 4)
+        launched = [k[0].name for k in log[n0:]]
+        a, b = dr.shard(np.arange(1001.0)), dr.shard(np.ones(1001))
+        wl.l2_distance(dr, a, b).run()
+        mesh.barrier()
+        q.put((rank, base.bounds, base.blocks[rank].shape, link.up is not None, link.dn is not None,
+               (link.up or {}).get("rows"), (link.dn or {}).get("rows"), link.epoch, launched,
+               a.array.base.bounds))
+        sharding.shutdown()
+
+
+def test_spmd_two_processes_plan_and_wire_without_a_gpu():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_spmd_dry_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (r0, r1) = res
+    assert r0[1] == r1[1] == [(0, 258), (258, 515)]                      # the same partition on both ranks
+    assert r0[2] == (258 + 2, 516) and r1[2] == (257 + 2, 516)          # owned rows + one halo row per side
+    assert (r0[3], r0[4], r1[3], r1[4]) == (False, True, True, False)   # neighbours: rank 0 below-only, rank 1 above-only
+    assert r0[6] == 259 and r1[5] == 260                                # each knows the other's block height
+    assert r0[7] == r1[7] == 4                                          # four halo-stencil steps, epochs agree
+    assert all(len(r[8]) == 4 and all(n.startswith("dr_stencil_") for n in r[8]) for r in res)   # one launch per step
+    assert r0[9] == r1[9] == [(0, 501), (501, 1001)]
