@@ -918,6 +918,20 @@ def _run_matmul(node):
     return result
 
 
+_SKINNY_FOLD_SRC = r"""
+extern "C" __global__ void __launch_bounds__(256) NAME(const TT* __restrict__ partial, TT* __restrict__ out,
+    TT* __restrict__ rowsum, i64 m, int n_out, int n, int ksplit) {
+  const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m * n_out) return;
+  const i64 row = i / n_out;
+  const int c = (int)(i - row * n_out);
+  ACC s = (ACC)0;
+  for (int q = 0; q < ksplit; ++q) s += (ACC)partial[((i64)q * m + row) * n_out + c];
+  if (c < n) out[row * n + c] = (TT)s; else rowsum[row] = (TT)s;
+}
+"""
+
+
 def _try_mm_skinny(node, pa, m, k, n, res_dt, with_rowsum=None):
     """A(M,K) @ B(K,n<=7) with a fused all-pairs producer -> gen_mm_skinny.  If a live, not yet
     evaluated ReduceEx(sum, A, axis=1) shares the same producer it is folded in as a virtual
@@ -976,13 +990,29 @@ def _try_mm_skinny(node, pa, m, k, n, res_dt, with_rowsum=None):
     a.ptr(b_dev.ptr)
     a.ptr(partial.ptr)
     launch(kern, dev, (-(-m // (TH * R)), ksplit, 1), TH, a)
-    total = ReduceEx(np.add, NPArray(partial), 0, False)._force()        # (m, n_out), fixed order
+    # one small kernel folds the K-split partials in split order (float32 accumulates in double) and
+    # writes the product and, if it rode along, the row sum: was a planned axis reduction plus two
+    # strided copies -- three launches and most of the host time of an n-body step
+    T = codegen.ctype(res_dt)
+    ACC = "double" if res_dt == np.float32 else T
+    fold = get_kernel(("mm_skinny_fold", res_dt.str), lambda name: _SKINNY_FOLD_SRC.replace("NAME", name)
+                      .replace("ACC", ACC).replace("TT", T))
+    d = dev if dev >= 0 else None
+    out = DeviceArray.empty((m, n), res_dt, d)
+    rs = DeviceArray.empty((m,), res_dt, d) if rowsum is not None else None
+    a = Args()
+    a.ptr(partial.ptr)
+    a.ptr(out.ptr)
+    a.ptr(rs.ptr if rs is not None else 0)
+    a.i64(m)
+    for v in (n_out, n, ksplit):
+        a.scalar(v, np.int32)
+    launch(fold, dev, max(1, -(-m * n_out // 256)), 256, a)
     node._stamp = _stamp_of(pa)
     if rowsum is not None:
-        rowsum.array = total[:, n].copy()
+        rowsum.array = rs
         rowsum._stamp = _stamp_of(pa)
-        return total[:, :n].copy()
-    return total
+    return out
 
 
 # --------------------------------------------------------------------------- assignment / copies
