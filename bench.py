@@ -199,7 +199,7 @@ class Verifier:
             self.failed.append(name)
 
 
-def verify_black_scholes(ver, dr, wl, host, call, put, n, chunk):
+def verify_black_scholes(ver, dr, wl, host, call, put, n, chunk, name="black_scholes_f32"):
     """call/put over ALL n positions: (i) every chunk-sized block of the outputs is bitwise equal
     to block 0 (device-side compare: the inputs repeat with period `chunk`), (ii) block 0 and a
     strided sample spanning the first and last GiB equal the oracle within the parity bar
@@ -227,7 +227,7 @@ def verify_black_scholes(ver, dr, wl, host, call, put, n, chunk):
     scale = np.spacing(np.maximum(host["S"], host["K"])).astype(np.float64)
     ours = max(float(np.max(np.abs(g[:chunk].get() - t) / scale)) for g, t in ((call, t64[0]), (put, t64[1])))
     theirs = max(float(np.max(np.abs(w - t) / scale)) for w, t in ((rc, t64[0]), (rp, t64[1])))
-    ver.put("black_scholes_f32", worst <= 1.0 and periodic, max_err_over_bar=worst,
+    ver.put(name, worst <= 1.0 and periodic, max_err_over_bar=worst,
             bar="16*eps32*max(S,K) = 16 ulp of the operand scale", all_blocks_bitwise_equal_block0=periodic,
             positions_checked=int(n), sampled_positions=int(idx.size),
             max_err_vs_float64_truth_in_ulp_of_max_S_K={"engine": ours, "oracle_numpy": theirs})
@@ -367,6 +367,25 @@ def bench_sharded(dr, wl, tm, ver, dev, peak, sync, rank, world, max_over_ranks,
         "collective": "ncclAllReduce(sum, 1 x f64) on libdrcuda's communicator",
         "roofline": _hbm_roof(16 * n, ms, peak, note="per GPU")}
     del a, b
+    # ---- C2 through the layer: S, K, T sharded (2^30 options per GPU, weak), call and put co-evaluated
+    # per row block by sharding.run_many -- one two-output kernel per block, no communication
+    nopt, chunk = (1 << 30, 1 << 22) if not quick else (1 << 24, 1 << 22)
+    hb = wl.make_inputs("black_scholes", chunk, seed=2 + rank)
+    S, K, T = (dr.sharding.from_local(dr.tile(dr.array(hb[k]), nopt // chunk)) for k in ("S", "K", "T"))
+
+    def bs_step():
+        call, put = wl.black_scholes(dr, S, K, T)
+        dr.evaluate(call, put)
+        return call, put
+    ms = max_over_ranks(tm.timed(lambda: bs_step(), 10, 3, sync))
+    call, put = bs_step()
+    mine = [dr.NPArray(x._force().base.blocks[rank]) for x in (call, put)]
+    verify_black_scholes(ver, dr, wl, hb, mine[0], mine[1], nopt, chunk, name="sharded_black_scholes")
+    out["black_scholes_f32_sharded"] = {
+        "scaling": "weak", "options_per_gpu": nopt, "ms": ms, "value": world * nopt / (ms * 1e-3), "unit": "options/s",
+        "collective": "none (elementwise regions are localised per row block)",
+        "roofline": _hbm_roof(BYTES_PER_OPTION * nopt, ms, peak, note="per GPU")}
+    del S, K, T, call, put, mine
     # ---- C4
     g, blk = (32768, 2048) if not quick else (4096, 2048)
     steps = 100

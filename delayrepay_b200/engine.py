@@ -616,9 +616,13 @@ def run(node):
 def run_many(nodes):
     """Co-evaluate: elementwise nodes sharing a shape go into ONE multi-output kernel."""
     groups = {}
+    sharded = [n for n in nodes if n.__dict__.get("_mesh") is not None]
+    if sharded:
+        from . import sharding
+        sharding.run_many(sharded)           # co-evaluated per row block, one kernel per block and shape
     for n in nodes:
         if n.__dict__.get("_mesh") is not None:
-            n._force()
+            continue
         elif n.kind == "ewise" and n.__dict__.get("array") is None:
             groups.setdefault(tuple(n.shape), [])
             if all(n is not m for m in groups[tuple(n.shape)]):

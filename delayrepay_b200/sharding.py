@@ -954,6 +954,56 @@ def run(node):
     raise NotImplementedError(kind)
 
 
+def run_many(nodes):
+    """engine.run_many for sharded nodes: lazy elementwise roots of one shape are localised TOGETHER
+    and co-evaluated per row block (Black-Scholes' call and put: one two-output kernel per block,
+    20 B/option, exactly as unsharded).  Everything else is evaluated on its own."""
+    from . import engine
+    groups = {}
+    for n in nodes:
+        if n.kind == "ewise" and n.__dict__.get("array") is None:
+            g = groups.setdefault(tuple(n.shape), [])
+            if all(n is not m for m in g):
+                g.append(n)
+        else:
+            n._force()
+    for group in groups.values():
+        if len(group) == 1:
+            group[0]._force()
+            continue
+        views = []
+        for n in group:
+            _shard_leaves(n, views, set())
+        if not views:
+            for n in group:
+                n._force()
+            continue
+        mesh = views[0].mesh
+        part = _partition(group[0], views)
+        nrows = group[0].shape[0]
+        _halo_reads.clear()
+        local = {}
+        for r in mesh.local:
+            i0, i1 = part[r]
+            if i1 > i0:
+                memo = {"__shape__": group[0].shape}          # shared: common subexpressions stay common
+                local[r] = [_localise(n, r, i0, i1, nrows, memo, mesh) for n in group]
+        _refresh_halos()
+        results = {r: None for r in mesh.local}
+        for r, roots in local.items():
+            engine.run_many(roots)
+            results[r] = [x._force() for x in roots]
+        for j, n in enumerate(group):
+            blocks = {}
+            for r in mesh.local:
+                if results[r] is not None:
+                    blocks[r] = results[r][j]
+                else:
+                    dev = mesh.devs[r]
+                    blocks[r] = DeviceArray.empty((0,) + tuple(n.shape[1:]), n.dtype, dev if dev >= 0 else None)
+            n.array = ShardView(ShardedBase.adopt(mesh, n.shape, n.dtype, [part[q] for q in range(mesh.world)], blocks))
+
+
 def _run_ewise(node):
     from . import engine
     views = []

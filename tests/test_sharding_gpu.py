@@ -212,6 +212,25 @@ def test_sharded_numpy_surface(gpu, mesh3):
         np.cumsum(s)                           # not a sharded operation: a clear error, no silent gather
 
 
+def test_sharded_black_scholes_is_one_kernel_per_block(gpu, mesh3):
+    """C2 through the layer: call and put are co-evaluated per row block (dr.evaluate ->
+    sharding.run_many), bit-identical to the unsharded engine, no communication."""
+    from delayrepay_b200 import engine
+    dr = gpu
+    n = (1 << 16) + 12
+    h = wl.make_inputs("black_scholes", n)
+    ref = wl.black_scholes(dr, *(dr.array(h[k]) for k in ("S", "K", "T")))
+    dr.evaluate(*ref)
+    S, K, T = (dr.shard(h[k]) for k in ("S", "K", "T"))
+    l0 = engine.stats["launches"]
+    call, put = wl.black_scholes(dr, S, K, T)
+    dr.evaluate(call, put)
+    assert engine.stats["launches"] - l0 == 3, "one two-output kernel per block"
+    assert type(call._force()).__name__ == "ShardView"
+    assert_bits_equal(call.get(), ref[0].get(), "sharded call")
+    assert_bits_equal(put.get(), ref[1].get(), "sharded put")
+
+
 def test_sharded_1d_stencil_generic_path(gpu, mesh3):
     """1-d arrays have a halo row too; their stencils take the generic temporary + copy path with
     the peer-copy exchange before each step."""
