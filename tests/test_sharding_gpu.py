@@ -227,17 +227,24 @@ def test_sharded_black_scholes_is_one_kernel_per_block(gpu, mesh3):
     dr.evaluate(call, put)
     assert engine.stats["launches"] - l0 == 3, "one two-output kernel per block"
     assert type(call._force()).__name__ == "ShardView"
-    assert_bits_equal(call.get(), ref[0].get(), "sharded call")
-    assert_bits_equal(put.get(), ref[1].get(), "sharded put")
+    names = {k.name for k in engine._kernels.values() if k.name == engine.last_kernel_name()}
+    assert any("dr_bulk_load_s(" in k.source for k in engine._kernels.values() if k.name in names), \
+        "the blocks run the vectorised staged kernel"
+    # same kernel as unsharded; only the <= 3 tail elements of each block take the scalar path
+    for got, want in ((call.get(), ref[0].get()), (put.get(), ref[1].get())):
+        same = np.mean(got.view(np.uint32) == want.view(np.uint32))
+        assert same >= 0.9998, same
+        bar = 16 * np.finfo(np.float32).eps * np.maximum(h["S"], h["K"])
+        assert np.all(np.abs(got.astype(np.float64) - want) <= bar)
 
 
 def test_sharded_1d_stencil_generic_path(gpu, mesh3):
-    """1-d arrays have a halo row too; their stencils take the generic temporary + copy path with
-    the peer-copy exchange before each step."""
+    """1-d arrays shard with a halo on request; their stencils take the generic temporary + copy
+    path with the peer-copy exchange before each step."""
     dr = gpu
     h = np.random.default_rng(3).standard_normal(1000)
-    v, want = dr.shard(h), h.copy()
-    assert v.array.base.H == 1
+    v, want = dr.shard(h, halo=1), h.copy()
+    assert v.array.base.H == 1 and dr.shard(h).array.base.H == 0
     for _ in range(4):
         v[1:-1] = 0.25 * (v[2:] + v[:-2]) + 0.5 * v[1:-1]
         want[1:-1] = 0.25 * (want[2:] + want[:-2]) + 0.5 * want[1:-1]
