@@ -1016,23 +1016,74 @@ def _run_ewise(node):
     nrows = node.shape[0]
     part = _partition(node, views)
     return ShardView(_evaluate_blocks(mesh, node, part, lambda r, i0, i1: _localise(
-        node, r, i0, i1, nrows, {"__shape__": node.shape}, mesh)))
+        node, r, i0, i1, nrows, {"__shape__": node.shape}, mesh), key=_graph_key("ew", node)))
 
 
-def _evaluate_blocks(mesh, node, part, build):
-    """One local evaluation per rank (``build(r, i0, i1)`` -> the local lazy node); the fresh
-    results become the blocks of a new sharded array -- no copy, plan cache and all."""
+_local_graphs = {}      # structural key -> {rank: (local root, extra lazy nodes to reset)}
+
+
+def _graph_key(tag, node, *more):
+    """Key under which the LOCAL lazy graphs of a sharded evaluation can be reused the next time
+    the same expression comes by: the expression's structural signature (which names every sharded
+    leaf by its storage), the identity of every other leaf, the scalar values.  None = do not
+    cache (cut points below, host operands not uploaded yet, ...)."""
+    d = node.__dict__
+    sig = d.get("_psig")
+    if sig is None or os.environ.get("DR_SHARD_NO_GRAPH_CACHE"):
+        return None
+    ident = []
+    for o in d["_pops"]:
+        if o.kind == "scalar":
+            ident.append((type(o.val).__name__, o.val))
+        else:
+            arr = o.array
+            if getattr(arr, "_is_shard_view", False):
+                ident.append(arr.layout_key())
+            elif isinstance(arr, DeviceArray):
+                ident.append(("D", id(arr.buf), arr.offset))
+            else:
+                return None                  # a host operand: a new leaf (and upload) per capture
+    return (tag, sig, tuple(ident)) + more
+
+
+def _evaluate_blocks(mesh, node, part, build, key=None):
+    """One local evaluation per rank (``build(r, i0, i1)`` -> the local lazy node, or a tuple
+    (node, extra nodes that receive results)); the fresh results become the blocks of a new
+    sharded array -- no copy, plan cache and all.  With a ``key`` the local lazy graphs are kept:
+    the next evaluation of the same expression over the same storage skips localisation and node
+    construction (their leaves are views of the blocks, which live as long as the arrays; a
+    replayed root is reset to "not evaluated" first)."""
     _halo_reads.clear()
-    lazy = {r: build(r, *part[r]) for r in mesh.local if part[r][1] > part[r][0]}
+    cache = _local_graphs.get(key) if key is not None else None
+    if cache is None:
+        cache = {}
+        for r in mesh.local:
+            if part[r][1] > part[r][0]:
+                got = build(r, *part[r])
+                cache[r] = got if isinstance(got, tuple) else (got, ())
+        cache["__reads__"] = set(_halo_reads)
+        cache["__part__"] = dict(part)
+        if key is not None:
+            if len(_local_graphs) > 128:
+                _local_graphs.clear()
+            _local_graphs[key] = cache
+    else:
+        _halo_reads.update(cache["__reads__"])
     _refresh_halos()
-    blocks = {}
+    blocks, extras = {}, {}
     for r in mesh.local:
-        if r in lazy:
-            blocks[r] = lazy[r]._force()
+        if r in cache:
+            root, more = cache[r]
+            blocks[r] = root._force()
+            extras[r] = [m.__dict__.get("array") for m in more]
+            for n in (root,) + tuple(more):          # lazy again for the next replay
+                n.__dict__.pop("array", None)
         else:
             dev = mesh.devs[r]
             blocks[r] = DeviceArray.empty((0,) + tuple(node.shape[1:]), node.dtype, dev if dev >= 0 else None)
-    return ShardedBase.adopt(mesh, node.shape, node.dtype, [part[r] for r in range(mesh.world)], blocks)
+    base = ShardedBase.adopt(mesh, node.shape, node.dtype, [part[r] for r in range(mesh.world)], blocks)
+    base._extras = extras
+    return base
 
 
 def _run_reduce(node):
@@ -1115,19 +1166,21 @@ def _run_contraction(node):
                     and cons.post is None and cons.__dict__.get("array") is None and cons.dtype == node.dtype:
                 rowsum = cons
                 break
-    local_sums = {}
-
     def build(r, i0, i1):
         la = _localise(a, r, i0, i1, nrows, {"__shape__": a.shape}, mesh)
+        extra = ()
         if rowsum is not None:
-            local_sums[r] = da.ReduceEx(np.add, la, 1, False)        # kept alive until the MMEx ran
-        return type(node)(la, _localise(b, r, 0, b.shape[0], -1, {"__shape__": b.shape}, mesh))
-    base = _evaluate_blocks(mesh, node, part, build)
-    if rowsum is not None and local_sums and all(n.__dict__.get("array") is not None for n in local_sums.values()):
+            extra = (da.ReduceEx(np.add, la, 1, False),)              # receives its result from the MMEx pass
+        return type(node)(la, _localise(b, r, 0, b.shape[0], -1, {"__shape__": b.shape}, mesh)), extra
+    key = None
+    if a.kind == "ewise" and b.kind == "leaf" and isinstance(b.array, DeviceArray):
+        key = _graph_key("mm", a, type(node).__name__, id(b.array.buf), b.array.offset, rowsum is not None)
+    base = _evaluate_blocks(mesh, node, part, build, key=key)
+    if rowsum is not None and base._extras and all(v and v[0] is not None for v in base._extras.values()):
         blocks = {}
         for r in mesh.local:
-            if r in local_sums:
-                blocks[r] = local_sums[r].array
+            if r in base._extras:
+                blocks[r] = base._extras[r][0]
             else:
                 dev = mesh.devs[r]
                 blocks[r] = DeviceArray.empty((0,), rowsum.dtype, dev if dev >= 0 else None)
