@@ -866,6 +866,139 @@ def _gen_nd_vec(name, prog, ndim, in_class, out_dts, V, threads, wide_index, scl
     return "\n".join(src) + "\n"
 
 
+# --------------------------------------------------------------------------- tile family
+def gen_tile(name, prog, in_class, out_dts, T=64, W=1, threads=256):
+    """Elementwise kernel over a 2-d space (R, C) in which some operands are *transposed* — they
+    walk contiguously along R, not along C (`X.T + X`, reference `delayarray.py:523-527` hands
+    `.T` to the backend array, so such operands arrive as stride-swapped leaves).  The general
+    `nd` kernel reads them a row pitch apart (2.1 TB/s).  Here a CTA owns a T x T tile: operands
+    of class 't' are loaded with the threads running along R (coalesced) into a padded shared
+    tile, then every thread evaluates the fused body with the threads running along C, reading
+    't' operands from shared memory and 'v' operands (contiguous along C) and the outputs
+    straight from / to global memory, coalesced.  ``W`` = 2: every thread handles two adjacent
+    elements of the contiguous direction with one 2-element vector access (4-byte types: 256
+    bytes per warp instruction; the planner checks the alignment).  Geometry: R, C, tiles along C,
+    tile count, then byte strides (rows, cols) per operand, inputs then outputs.
+    Classes: 'b' one value for the whole space, 't' via the shared tile, 'v' / 's' direct."""
+    arrays, scalars = prog.arrays, prog.scalars
+    n_ops = len(arrays) + len(out_dts)
+    lanes = T // W                       # threads along the contiguous direction
+    step = threads // lanes
+    passes = T // step
+    src = []
+    w = src.append
+    w(f"struct Geo_{name} {{ i64 R; i64 C; i64 tiles_c; i64 ntiles; i64 stride[{n_ops}][2]; }};")
+    params = [f"const Geo_{name} g"]
+    for i, a in enumerate(arrays):
+        params.append(f"const char* __restrict__ in{i}")
+    for j, (_, dt) in enumerate(scalars):
+        params.append(f"const {ctype(dt)} s{j}")
+    for o, dt in enumerate(out_dts):
+        params.append(f"char* __restrict__ out{o}")
+    body = emit_body(prog)
+    w(f'extern "C" __global__ void __launch_bounds__({threads}) {name}({", ".join(params)}) {{')
+    for i, (a, c) in enumerate(zip(arrays, in_class)):
+        if c == "t":
+            w(f"  __shared__ {ctype(a.dtype)} tile{i}[{T}][{T + 1}];")
+        elif c == "b":
+            w(f"  const {ctype(a.dtype)} x{i} = *reinterpret_cast<const {ctype(a.dtype)}*>(in{i});")
+    w(f"  const int lx = (threadIdx.x % {lanes}) * {W}, ly = threadIdx.x / {lanes};")
+    w("  for (i64 t = blockIdx.x; t < g.ntiles; t += gridDim.x) {")
+    w("    const i64 tr = t / g.tiles_c, tc = t - tr * g.tiles_c;")
+    w(f"    const i64 r0 = tr * {T}, c0 = tc * {T};")
+    staged = [(i, ctype(a.dtype)) for i, (a, c) in enumerate(zip(arrays, in_class)) if c == "t"]
+    direct = [(i, ctype(a.dtype)) for i, (a, c) in enumerate(zip(arrays, in_class)) if c == "v"]
+    w("    {                                                  // threads along R: the transposed operands")
+    w("      const i64 r = r0 + lx;")
+    for i, Tn in staged:
+        w(f"      const char* p{i} = in{i} + r * g.stride[{i}][0] + (c0 + ly) * g.stride[{i}][1];")
+    if W == 1:
+        w(f"#pragma unroll\n      for (int k = 0; k < {passes}; ++k) {{")
+        w(f"        if (r < g.R && c0 + ly + k * {step} < g.C) {{")
+        for i, Tn in staged:
+            w(f"          tile{i}[ly + k * {step}][lx] = *reinterpret_cast<const {Tn}*>"
+              f"(p{i} + (i64)(k * {step}) * g.stride[{i}][1]);")
+        w("        }")
+        w("      }")
+    else:
+        # every load of the tile is issued before the first shared-memory store (the vector
+        # accessors are asm statements the compiler keeps in order)
+        for i, Tn in staged:
+            w(f"      Vec<{Tn}, {W}> h{i}[{passes}];")
+        w(f"#pragma unroll\n      for (int k = 0; k < {passes}; ++k) {{")
+        w(f"        if (c0 + ly + k * {step} < g.C) {{")
+        for i, Tn in staged:
+            at = f"reinterpret_cast<const {Tn}*>(p{i} + (i64)(k * {step}) * g.stride[{i}][1])"
+            w(f"          if (r + {W - 1} < g.R) h{i}[k] = dr_ld<true, {Tn}, {W}>({at});")
+            w(f"          else if (r < g.R) h{i}[k].v[0] = *{at};")
+        w("        }")
+        w("      }")
+        w(f"#pragma unroll\n      for (int k = 0; k < {passes}; ++k) {{")
+        for i, Tn in staged:
+            for e in range(W):
+                w(f"        tile{i}[ly + k * {step}][lx + {e}] = h{i}[k].v[{e}];")
+        w("      }")
+    w("    }")
+    w("    __syncthreads();")
+    w("    {                                                  // threads along C: evaluate and store")
+    w("      const i64 c = c0 + lx;")
+    for i, (a, c) in enumerate(zip(arrays, in_class)):
+        if c in "vs":
+            w(f"      const char* p{i} = in{i} + (r0 + ly) * g.stride[{i}][0] + c * g.stride[{i}][1];")
+    for o in range(len(out_dts)):
+        k = len(arrays) + o
+        w(f"      char* q{o} = out{o} + (r0 + ly) * g.stride[{k}][0] + c * g.stride[{k}][1];")
+    if W > 1:
+        for i, Tn in direct:
+            w(f"      Vec<{Tn}, {W}> vx{i}[{passes}];")
+        if direct:
+            w(f"#pragma unroll\n      for (int k = 0; k < {passes}; ++k) {{")
+            w(f"        if (r0 + ly + k * {step} < g.R) {{")
+            for i, Tn in direct:
+                at = f"reinterpret_cast<const {Tn}*>(p{i} + (i64)(k * {step}) * g.stride[{i}][0])"
+                w(f"          if (c + {W - 1} < g.C) vx{i}[k] = dr_ld<true, {Tn}, {W}>({at});")
+                w(f"          else if (c < g.C) vx{i}[k].v[0] = *{at};")
+            w("        }")
+            w("      }")
+    w(f"#pragma unroll\n      for (int k = 0; k < {passes}; ++k) {{")
+    w(f"        if (r0 + ly + k * {step} < g.R && c < g.C) {{")
+    for o, dt in enumerate(out_dts):
+        if W > 1:
+            w(f"          Vec<{ctype(dt)}, {W}> vr{o};")
+    for e in range(W):
+        w("          {" if e == 0 else f"          if (c + {e} < g.C) {{")
+        for i, (a, c) in enumerate(zip(arrays, in_class)):
+            Tn = ctype(a.dtype)
+            if c == "t":
+                w(f"            const {Tn} x{i} = tile{i}[lx + {e}][ly + k * {step}];")
+            elif c == "v" and W > 1:
+                w(f"            const {Tn} x{i} = vx{i}[k].v[{e}];")
+            elif c in "vs":
+                w(f"            const {Tn} x{i} = *reinterpret_cast<const {Tn}*>(p{i} + (i64)(k * {step}) * "
+                  f"g.stride[{i}][0] + (i64){e} * g.stride[{i}][1]);")
+        for line in body:
+            w(f"            {line}")
+        for o, (r, dt) in enumerate(zip(prog.roots, out_dts)):
+            if W > 1:
+                w(f"            vr{o}.v[{e}] = {_store_expr(prog, r, dt)};")
+            else:
+                w(f"            *reinterpret_cast<{ctype(dt)}*>(q{o} + (i64)(k * {step}) * "
+                  f"g.stride[{len(arrays) + o}][0]) = {_store_expr(prog, r, dt)};")
+        w("          }")
+    if W > 1:
+        for o, dt in enumerate(out_dts):
+            at = f"reinterpret_cast<{ctype(dt)}*>(q{o} + (i64)(k * {step}) * g.stride[{len(arrays) + o}][0])"
+            w(f"          if (c + {W - 1} < g.C) dr_st<true, {ctype(dt)}, {W}>({at}, vr{o});")
+            w(f"          else *{at} = vr{o}.v[0];")
+    w("        }")
+    w("      }")
+    w("    }")
+    w("    __syncthreads();")
+    w("  }")
+    w("}")
+    return "\n".join(src) + "\n"
+
+
 # --------------------------------------------------------------------------- rows family
 def _emit_lane_operands(w, arrays, in_class, V, indent):
     """inside the per-lane loop `e`: bind x<i> for every non-broadcast operand"""

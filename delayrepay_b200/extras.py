@@ -4,6 +4,8 @@ CUDA C++ template specialised by dtype and compiled through the same NVRTC/cubin
 (engine.get_kernel).  Reference: these are the eager CuPy calls of delayarray.py:555-558 (cumsum),
 random.py:8-13 (cuRAND) and fft.py:12 (cuFFT).
 """
+import os
+
 import numpy as np
 
 from . import engine
@@ -150,6 +152,285 @@ extern "C" __global__ void __launch_bounds__(256) NAME_final(const TIN* __restri
   for (int k = 0; k < ITEMS; ++k) if (base + k < n) out[base + k] = before + v[k];
 }
 '''
+# Second-generation scans: 128-bit accesses laid out per warp and, for the 1-d case, ONE pass over
+# the data.  A tile = THREADS * NV vectors of VE = 16 / sizeof(TIN) elements; warp w owns a
+# contiguous chunk of it and lane l its vectors j * 32 + l (every load / store instruction of a
+# warp covers 512 contiguous bytes).  Element order inside a chunk is (j, lane, e): per j a lane-
+# local scan, a shuffle scan over the lanes and the running total of the earlier j.
+#
+# NAME_chain (1-d): G co-resident CTAs walk the tiles round by round (tile t = round * G + p).
+# A tile publishes its total (agg[t], flag[t]) as soon as its data is reduced, then waits for the
+# totals of the tiles in front of it IN ITS OWN ROUND and for the round's carry; the last tile of
+# a round publishes the next carry.  Nothing is read twice (8 B / element for float32 instead of
+# 12), the next tile's loads are in flight while a CTA waits, and — unlike decoupled look-back —
+# every prefix is the same fixed-order sum on every run: the result is reproducible bit for bit.
+_SCAN2_SRC = r'''
+#define VE (16 / (int)sizeof(TIN))
+#define NV NVVAL
+#define SV ((int)sizeof(TACC) * VE / 16)
+typedef dr_raw<16> V16;
+union InVec { V16 q; TIN e[VE]; __device__ InVec() {} };
+union OutVec { V16 q[SV]; TACC e[VE]; __device__ OutVec() {} };
+
+template <typename T> __device__ __forceinline__ T dr_shfl_idx(T v, int src) {
+  if (sizeof(T) == 8) {
+    union { T t; struct { u32 lo, hi; } s; } u;
+    u.t = v;
+    u.s.lo = __shfl_sync(0xffffffffu, u.s.lo, src);
+    u.s.hi = __shfl_sync(0xffffffffu, u.s.hi, src);
+    return u.t;
+  } else {
+    union { T t; u32 w; } u;
+    u.w = 0; u.t = v;
+    u.w = __shfl_sync(0xffffffffu, u.w, src);
+    return u.t;
+  }
+}
+// A published total is ONE 16-byte record {value, flag}, written and polled with single 128-bit
+// relaxed accesses (single-copy atomic): no fence on either side.  A fence, or the release /
+// acquire pair of a separate flag word, waits for the thread's outstanding loads — here the
+// prefetch of the next tile, i.e. a full DRAM latency on the critical path of every round
+// (measured: 10.5 us per round with fences, see DESIGN.md).
+struct alignas(16) ScRec { unsigned long long value, flag; };
+__device__ __forceinline__ void sc_publish(ScRec* p, TACC v) {
+  union { TACC t; unsigned long long w; } u; u.w = 0ull; u.t = v;
+  asm volatile("{ .reg .b128 q; mov.b128 q, {%1, %2}; st.relaxed.gpu.global.b128 [%0], q; }"
+               :: "l"(p), "l"(u.w), "l"(1ull) : "memory");
+}
+__device__ __forceinline__ bool sc_peek(const ScRec* p, TACC& v) {
+  unsigned long long lo, hi;
+  asm volatile("{ .reg .b128 q; ld.relaxed.gpu.global.b128 q, [%2]; mov.b128 {%0, %1}, q; }"
+               : "=l"(lo), "=l"(hi) : "l"(p) : "memory");
+  union { TACC t; unsigned long long w; } u; u.w = lo;
+  v = u.t;
+  return hi != 0ull;
+}
+// vectors of one thread for the tile that starts at `src` and has `rem` elements left in its row
+// (a full tile takes the path without a single bounds test)
+template <int THREADS>
+__device__ __forceinline__ void sc_load(const TIN* __restrict__ src, int rem, V16 (&raw)[NV]) {
+  const int off = ((threadIdx.x >> 5) * (32 * NV) + (threadIdx.x & 31)) * VE;
+  if (rem >= THREADS * NV * VE) {
+    const V16* q = reinterpret_cast<const V16*>(src + off);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) raw[j] = dr_ld_raw<true>(q + j * 32);
+  } else {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int idx = off + j * 32 * VE;
+      if (idx + VE <= rem) raw[j] = dr_ld_raw<true>(reinterpret_cast<const V16*>(src + idx));
+      else {
+        InVec u;
+#pragma unroll
+        for (int e = 0; e < VE; ++e) u.e[e] = idx + e < rem ? src[idx + e] : (TIN)0;
+        raw[j] = u.q;
+      }
+    }
+  }
+}
+// inclusive prefixes relative to the start of the warp's chunk; returns the chunk total
+__device__ __forceinline__ TACC sc_warp_scan(const V16 (&raw)[NV], TACC (&v)[NV][VE]) {
+  const int lane = threadIdx.x & 31;
+  TACC run = (TACC)0;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    InVec u; u.q = raw[j];
+    TACC s = (TACC)0;
+#pragma unroll
+    for (int e = 0; e < VE; ++e) { s += (TACC)u.e[e]; v[j][e] = s; }
+    TACC x = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const TACC y = dr_shfl_up(x, o); if (lane >= o) x += y; }
+    TACC ex = dr_shfl_up(x, 1);
+    if (lane == 0) ex = (TACC)0;
+    const TACC base = run + ex;
+#pragma unroll
+    for (int e = 0; e < VE; ++e) v[j][e] = base + v[j][e];
+    run += dr_shfl_idx(x, 31);
+  }
+  return run;
+}
+// warp 0: exclusive scan of the warp totals (sW -> sEx), returns the tile total in every lane
+template <int THREADS>
+__device__ __forceinline__ TACC sc_block_offsets(const TACC* sW, TACC* sEx) {
+  const int lane = threadIdx.x & 31;
+  const TACC w = lane < THREADS / 32 ? sW[lane] : (TACC)0;
+  TACC x = w;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const TACC y = dr_shfl_up(x, o); if (lane >= o) x += y; }
+  TACC ex = dr_shfl_up(x, 1);
+  if (lane == 0) ex = (TACC)0;
+  sEx[lane] = ex;
+  return dr_shfl_idx(x, 31);
+}
+template <int THREADS>
+__device__ __forceinline__ void sc_store(TACC* __restrict__ dst, int rem, const TACC (&v)[NV][VE], TACC add) {
+  const int off = ((threadIdx.x >> 5) * (32 * NV) + (threadIdx.x & 31)) * VE;
+  if (rem >= THREADS * NV * VE) {
+    V16* q = reinterpret_cast<V16*>(dst + off);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      OutVec u;
+#pragma unroll
+      for (int e = 0; e < VE; ++e) u.e[e] = add + v[j][e];
+#pragma unroll
+      for (int k = 0; k < SV; ++k) dr_st_raw<true>(q + j * 32 * SV + k, u.q[k]);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int idx = off + j * 32 * VE;
+      OutVec u;
+#pragma unroll
+      for (int e = 0; e < VE; ++e) u.e[e] = add + v[j][e];
+      if (idx + VE <= rem) {
+#pragma unroll
+        for (int k = 0; k < SV; ++k) dr_st_raw<true>(reinterpret_cast<V16*>(dst + idx) + k, u.q[k]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < VE; ++e) if (idx + e < rem) dst[idx + e] = u.e[e];
+      }
+    }
+  }
+}
+
+// total of the warp's chunk (local sums, one butterfly)
+__device__ __forceinline__ TACC sc_warp_total(const V16 (&raw)[NV]) {
+  const int lane = threadIdx.x & 31;
+  TACC s = (TACC)0;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    InVec u; u.q = raw[j];
+#pragma unroll
+    for (int e = 0; e < VE; ++e) s += (TACC)u.e[e];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += dr_shfl_idx(s, lane ^ o);
+  return s;
+}
+__device__ __forceinline__ int sc_rem(i64 n, i64 base, i64 tile) {
+  const i64 left = n - base;
+  return left < tile ? (int)left : (int)tile;
+}
+
+extern "C" __global__ void __launch_bounds__(CTHREADS, CPS) NAME_chain(const TIN* __restrict__ in,
+    TACC* __restrict__ out, i64 n, i64 ntiles, ScRec* agg) {
+  __shared__ TACC sW[32], sWn[32], sEx[32], sExn[32], sLt[32], sAll[32];
+  constexpr i64 TILE = (i64)CTHREADS * NV * VE;
+  const int G = gridDim.x, p = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  V16 cur[NV], nxt[NV];
+  // prologue: the totals of the CTA's first SLACK tiles; the tile after them starts to load
+#pragma unroll 1
+  for (int r = 0; r < SLACK; ++r) {
+    const i64 t = (i64)p + (i64)r * G;
+    if (t >= ntiles) break;
+    sc_load<CTHREADS>(in + t * TILE, sc_rem(n, t * TILE, TILE), nxt);
+    const TACC W0 = sc_warp_total(nxt);
+    if (lane == 0) sWn[warp] = W0;
+    __syncthreads();
+    if (warp == 0) {
+      const TACC total = sc_block_offsets<CTHREADS>(sWn, sExn);
+      if (lane == 0) sc_publish(agg + t, total);
+    }
+    __syncthreads();
+  }
+  if ((i64)p + (i64)SLACK * G < ntiles)
+    sc_load<CTHREADS>(in + ((i64)p + (i64)SLACK * G) * TILE, sc_rem(n, ((i64)p + (i64)SLACK * G) * TILE, TILE), nxt);
+  TACC carry = (TACC)0;
+  i64 rho = 0;
+  for (i64 t = p; t < ntiles; t += G, ++rho) {
+    const i64 ahead = t + (i64)SLACK * G;
+    const bool has_next = ahead < ntiles;
+    // a tile is read twice: SLACK rounds ahead for its total (from HBM, prefetched a round earlier
+    // still), and now for the scan itself (from L2: it was read SLACK + 1 rounds ago)
+    sc_load<CTHREADS>(in + t * TILE, sc_rem(n, t * TILE, TILE), cur);
+    if (has_next) {
+      const TACC Wn = sc_warp_total(nxt);
+      if (lane == 0) sWn[warp] = Wn;
+    }
+    if (ahead + G < ntiles)
+      sc_load<CTHREADS>(in + (ahead + G) * TILE, sc_rem(n, (ahead + G) * TILE, TILE), nxt);
+    TACC v[NV][VE];
+    const TACC W = sc_warp_scan(cur, v);
+    if (lane == 0) sW[warp] = W;
+    __syncthreads();
+    if (warp == 0) {
+      if (has_next) {                                   // published SLACK rounds before it is needed
+        const TACC total = sc_block_offsets<CTHREADS>(sWn, sExn);
+        if (lane == 0) sc_publish(agg + ahead, total);
+      }
+      sc_block_offsets<CTHREADS>(sW, sEx);
+    }
+    // all totals of this round, one record per thread (a single round trip to L2): the tiles in
+    // front of this one give its prefix, all of them the next carry — the same fixed-order sums
+    // in every CTA, so no carry has to be communicated and every run produces the same bits
+    const ScRec* round = agg + rho * G;
+    const i64 left = ntiles - rho * G;
+    const int Gr = left < G ? (int)left : G;
+    TACC lt, all;
+    for (long long spins = 0;; ++spins) {
+      bool ok = true;
+      lt = (TACC)0; all = (TACC)0;
+      for (int q = threadIdx.x; q < Gr; q += CTHREADS) {      // one pass: G <= CTHREADS
+        TACC a;
+        ok = ok & sc_peek(round + q, a);
+        all += a;
+        if (q < p) lt += a;
+      }
+      if (__syncthreads_and(ok)) break;
+      if (spins > 100000000ll) __trap();                // tens of seconds: a lost peer, not a slow one
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { lt += dr_shfl_idx(lt, lane ^ o); all += dr_shfl_idx(all, lane ^ o); }
+    if (lane == 0) { sLt[warp] = lt; sAll[warp] = all; }
+    __syncthreads();
+    // the warps' partial sums, again in a fixed order (every warp repeats the same butterfly)
+    TACC prefix = lane < CTHREADS / 32 ? sLt[lane] : (TACC)0;
+    TACC round_total = lane < CTHREADS / 32 ? sAll[lane] : (TACC)0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      prefix += dr_shfl_idx(prefix, lane ^ o);
+      round_total += dr_shfl_idx(round_total, lane ^ o);
+    }
+    prefix = carry + prefix;
+    carry += round_total;
+    sc_store<CTHREADS>(out + t * TILE, sc_rem(n, t * TILE, TILE), v, prefix + sEx[warp]);
+  }
+}
+
+// rows of a matrix scanned along the contiguous axis: one CTA per row, tile by tile with a carry
+extern "C" __global__ void __launch_bounds__(256, 4) NAME_rowscan2(const TIN* __restrict__ in,
+    TACC* __restrict__ out, i64 rows, i64 n) {
+  __shared__ TACC sW[32], sEx[32];
+  __shared__ TACC sTotal;
+  constexpr i64 TILE = (i64)256 * NV * VE;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (i64 r = blockIdx.x; r < rows; r += gridDim.x) {
+    const TIN* p = in + r * n;
+    TACC* q = out + r * n;
+    TACC carry = (TACC)0;
+    V16 cur[NV], nxt[NV];
+    sc_load<256>(p, sc_rem(n, 0, TILE), cur);
+    for (i64 base = 0; base < n; base += TILE) {
+      if (base + TILE < n) sc_load<256>(p + base + TILE, sc_rem(n, base + TILE, TILE), nxt);
+      TACC v[NV][VE];
+      const TACC W = sc_warp_scan(cur, v);
+      if (lane == 0) sW[warp] = W;
+      __syncthreads();
+      if (warp == 0) {
+        const TACC total = sc_block_offsets<256>(sW, sEx);
+        if (lane == 0) sTotal = total;
+      }
+      __syncthreads();
+      sc_store<256>(q + base, sc_rem(n, base, TILE), v, carry + sEx[warp]);
+      carry += sTotal;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) cur[j] = nxt[j];
+    }
+    __syncthreads();
+  }
+}
+'''
 _SHFL_UP = r'''
 template <typename T> __device__ __forceinline__ T dr_shfl_up(T v, int delta) {
   if (sizeof(T) == 8) {
@@ -168,9 +449,15 @@ template <typename T> __device__ __forceinline__ T dr_shfl_up(T v, int delta) {
 '''
 
 
+_scan_sets = {}                 # key -> {suffix: Kernel}: built once (the source hash alone costs ~0.7 ms)
+
+
 def _scan_kernels(in_dt, acc_dt):
     # one module holds all four entry points; load each by name
     key = ("scan", np.dtype(in_dt).str, np.dtype(acc_dt).str)
+    hit = _scan_sets.get(key)
+    if hit is not None:
+        return hit
     name = engine.kernel_name(key)
     src = _SHFL_UP + _SCAN_SRC.replace("NAME", name).replace("TIN", ctype(in_dt)).replace("TACC", ctype(acc_dt))
     _, cubin = engine.compile_source(name, src)
@@ -181,7 +468,61 @@ def _scan_kernels(in_dt, acc_dt):
         if k is None:
             k = engine._kernels[key + (suffix,)] = engine.Kernel(f"{name}_{suffix}", src, cubin, {})
         out[suffix] = k
+    _scan_sets[key] = out
     return out
+
+
+# 2 CTAs of 512 threads per SM; totals are published one round ahead.  Measured alternatives
+# (profiles/r2_scan_chain_experiments.txt): 1024 x 1 and 256 x 4 are within 2 %, 2 or 3 rounds
+# ahead are 5 - 8 % slower (the second read starts to miss L2)
+_CHAIN_THREADS, _CHAIN_CPS, _CHAIN_SLACK = 512, 2, 1
+
+
+def _scan2_kernels(in_dt, acc_dt, sm_count):
+    """(kernels, NV) of the second-generation scans for one (input, accumulator) type pair."""
+    in_dt, acc_dt = np.dtype(in_dt), np.dtype(acc_dt)
+    ve = 16 // in_dt.itemsize
+    nv = max(1, min(4, 64 // (ve * acc_dt.itemsize)))
+    key = ("scan2", in_dt.str, acc_dt.str, nv, _CHAIN_THREADS, _CHAIN_CPS, _CHAIN_SLACK)
+    hit = _scan_sets.get(key)
+    if hit is not None:
+        return hit, nv
+    name = engine.kernel_name(key)
+    src = _SHFL_UP + (_SCAN2_SRC.replace("NAME", name).replace("NVVAL", str(nv)).replace("SLACK", str(_CHAIN_SLACK))
+                      .replace("CTHREADS", str(_CHAIN_THREADS)).replace("CPS", str(_CHAIN_CPS))
+                      .replace("TIN", ctype(in_dt)).replace("TACC", ctype(acc_dt)))
+    _, cubin = engine.compile_source(name, src)
+    out = {}
+    for suffix in ("chain", "rowscan2"):
+        k = engine._kernels.get(key + (suffix,))
+        if k is None:
+            k = engine._kernels[key + (suffix,)] = engine.Kernel(f"{name}_{suffix}", src, cubin, {})
+        out[suffix] = k
+    _scan_sets[key] = out
+    return out, nv
+
+
+def _chain_scan(src, out, n, in_dt, acc_dt):
+    """1-d inclusive scan of `n` contiguous elements in one pass (NAME_chain above)."""
+    dev = src.dev
+    st = engine.dev_state(dev)
+    ks, nv = _scan2_kernels(in_dt, acc_dt, st.sm_count)
+    tile = _CHAIN_THREADS * nv * (16 // in_dt.itemsize)
+    ntiles = -(-n // tile)
+    kern = ks["chain"]
+    G = st.sm_count * _CHAIN_CPS
+    if dev >= 0 and kern.blocks_per_sm(dev, _CHAIN_THREADS) < _CHAIN_CPS:
+        return False                      # the CTAs of a round must be co-resident
+    G = min(G, ntiles)
+    rounds = -(-ntiles // G)
+    d = dev if dev >= 0 else None
+    recs = DeviceArray.empty((ntiles, 2), np.uint64, d)                   # {total, flag} per tile
+    if dev >= 0:
+        engine.check(engine.lib.drc_memset_async(dev, 0, recs.ptr, 0, recs.nbytes))
+    a = Args()
+    a.ptr(src.ptr); a.ptr(out.ptr); a.i64(n); a.i64(ntiles); a.ptr(recs.ptr)
+    launch(kern, dev, G, _CHAIN_THREADS, a)
+    return True
 
 
 def _grid_1d(n):
@@ -207,6 +548,15 @@ def cumsum(arr, axis=None):
         return out
     ks = _scan_kernels(in_dt, acc_dt)
     d = dev if dev >= 0 else None
+    gen2 = not os.environ.get("DR_SCAN_GEN1") and src.ptr % 16 == 0
+    if gen2 and inner == 1 and outer >= 64 and n >= 1024 and (n * in_dt.itemsize) % 16 == 0:
+        ks2, _ = _scan2_kernels(in_dt, acc_dt, engine.dev_state(dev).sm_count)
+        a = Args()
+        a.ptr(src.ptr); a.ptr(out.ptr); a.i64(outer); a.i64(n)
+        launch(ks2["rowscan2"], dev, min(outer, 148 * 8), 256, a)
+        return out
+    if gen2 and outer == 1 and inner == 1 and n >= (1 << 20) and _chain_scan(src, out, n, in_dt, acc_dt):
+        return out
     if inner == 1 and outer >= 64 and n >= 64:
         a = Args()
         a.ptr(src.ptr); a.ptr(out.ptr); a.i64(outer); a.i64(n)

@@ -295,6 +295,51 @@ def resolve_layout(prog, outs, inner_vectors=True):
     return lay
 
 
+def tile_classes(prog, outs, lay):
+    """An `nd` layout over a 2-d space whose outputs are contiguous along the last dimension and
+    in which at least one operand is contiguous along the FIRST one (a transposed matrix): the
+    operand classes and tile edge for codegen.gen_tile, or None."""
+    if lay.family != "nd" or lay.vec_ok or len(lay.shape) != 2 or not outs or lay.total >= (1 << 40):
+        return None
+    if lay.shape[0] < 32 or lay.shape[1] < 32:
+        return None
+    for o, st in zip(outs, lay.out_strides):
+        if st[1] != o.dtype.itemsize:
+            return None
+    cls, staged = [], []
+    for a, st in zip(prog.arrays, lay.in_strides):
+        item = a.dtype.itemsize
+        if st[0] == 0 and st[1] == 0:
+            cls.append("b")
+        elif st[1] == item:
+            cls.append("v")
+        elif st[0] == item and item in (4, 8):
+            cls.append("t")
+            staged.append(item)
+        else:
+            cls.append("s")
+    if not staged:
+        return None
+    T = 64 if max(staged) == 4 else 32
+    if sum(T * (T + 1) * i for i in staged) > 40 * 1024:
+        T = 32
+        if sum(T * (T + 1) * i for i in staged) > 40 * 1024:
+            return None
+    # two elements per thread (one 2-element vector access) when every staged operand is 4 bytes
+    # wide and every vector access would be aligned
+    W = 2 if T == 64 and max(staged) == 4 else 1
+    if W == 2:
+        for a, st, c in zip(prog.arrays, lay.in_strides, cls):
+            al = 2 * a.dtype.itemsize
+            if (c == "v" and (a.ptr % al or st[0] % al)) or (c == "t" and (a.ptr % al or st[1] % al)):
+                W = 1
+        for o, st in zip(outs, lay.out_strides):
+            al = 2 * o.dtype.itemsize
+            if o.ptr % al or st[0] % al:
+                W = 1
+    return tuple(cls), T, W
+
+
 def _try_inner_vectors(prog, outs, lay):
     """nd family with 128-bit accesses along the innermost collapsed dimension: every operand is
     either contiguous along it ('v': stride == itemsize, vector load/store) or does not move along

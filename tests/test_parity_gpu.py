@@ -918,3 +918,79 @@ def test_signed_integer_overflow_wraps_like_numpy(gpu):
                 big = rng.integers(info.max // 4, info.max, 1003, dtype=dt)
                 assert int(np.sum(gpu.array(big))) == int(np.sum(big))            # int64 accumulator wraps too
                 assert np.prod(gpu.array(big)).get() == np.prod(big)
+
+
+def test_tile_family_transposed_operands_bit_exact(gpu):
+    """`X.T + X` and friends go through the shared-memory tile kernel (codegen.gen_tile): same
+    arithmetic as the strided kernel, so everything is bit-exact against NumPy."""
+    from delayrepay_b200 import engine
+    rng = np.random.default_rng(101)
+    for dt in (np.float32, np.float64, np.int32, np.int64):
+        for r, c in ((64, 64), (257, 130), (33, 1000), (1000, 33), (640, 448)):
+            a = (rng.standard_normal((r, c)) * 100).astype(dt)
+            b = (rng.standard_normal((c, r)) * 100).astype(dt)
+            v = (rng.standard_normal(c) * 100).astype(dt)
+            A, B, V = gpu.array(a), gpu.array(b), gpu.array(v)
+            got = (B.T + A).get()
+            assert engine.last_kernel_name().startswith("dr_tile_"), engine.last_kernel_name()
+            assert_bits_equal(got, b.T + a, f"X.T + X {dt} {r}x{c}")
+            assert_bits_equal((B.T * 3 - A * V).get(), b.T * 3 - a * v, f"row vector beside a transposed operand {dt}")
+            assert_bits_equal(((B.T > A) & (A > 0)).get(), (b.T > a) & (a > 0), f"bool output {dt}")
+            assert_bits_equal((B.T + B.T * B.T).get(), b.T + b.T * b.T, f"only transposed operands {dt}")
+            assert_bits_equal(B.T.copy().get(), b.T, "plain transpose")
+    # a column block of a wider matrix, transposed; mixed widths (float32 tile beside float64 rows)
+    w = rng.standard_normal((300, 500)).astype(np.float32)
+    a = rng.standard_normal((200, 300))
+    W, A = gpu.array(w), gpu.array(a)
+    assert_bits_equal((W[:, 100:300].T + A).get(), w[:, 100:300].T + a, "transposed column block, mixed dtypes")
+    assert engine.last_kernel_name().startswith("dr_tile_")
+    # two roots over the same transposed operand stay one kernel
+    s, d = gpu.evaluate(W.T + 1.0, W.T * 2.0)
+    assert_bits_equal(s.get(), w.T + np.float32(1.0), "co-evaluated root 0")
+    assert_bits_equal(d.get(), w.T * np.float32(2.0), "co-evaluated root 1")
+    # transcendental body and the plan cache (second call replays the prepared launch)
+    for _ in range(2):
+        got = np.exp(W.T * 0.01).get()
+        assert_ulp(got, np.exp((w.T * np.float32(0.01)).astype(np.float64)).astype(np.float32), 2,
+                   "exp over a transposed operand")
+
+
+def test_generation2_scans(gpu):
+    """One-pass chained 1-d scan and the vectorised row scan (extras._SCAN2_SRC): integers exact,
+    floats within the reduction tolerance, and bit-reproducible from run to run."""
+    from delayrepay_b200 import engine
+    rng = np.random.default_rng(202)
+    for n in ((1 << 20), (1 << 20) + 3, 5_000_001, (1 << 24) + 8191):
+        xi = rng.integers(-1000, 1000, n).astype(np.int32)
+        assert_bits_equal(np.cumsum(gpu.array(xi)).get(), np.cumsum(xi), f"int32 chained scan {n}")
+        assert engine.last_kernel_name().endswith("_chain"), engine.last_kernel_name()
+        xl = rng.integers(-10 ** 12, 10 ** 12, n)
+        assert_bits_equal(np.cumsum(gpu.array(xl)).get(), np.cumsum(xl), f"int64 chained scan {n}")
+        xb = rng.integers(0, 2, n).astype(bool)
+        assert_bits_equal(np.cumsum(gpu.array(xb)).get(), np.cumsum(xb), f"bool chained scan {n}")
+        xd = rng.standard_normal(n)
+        first = np.cumsum(gpu.array(xd)).get()
+        np.testing.assert_allclose(first, np.cumsum(xd), rtol=1e-11, atol=1e-8)
+        assert_bits_equal(np.cumsum(gpu.array(xd)).get(), first, "float64 scan is reproducible")
+        xf = rng.random(n).astype(np.float32)
+        first = np.cumsum(gpu.array(xf)).get()
+        np.testing.assert_allclose(first, np.cumsum(xf.astype(np.float64)), rtol=1e-5)
+        assert_bits_equal(np.cumsum(gpu.array(xf)).get(), first, "float32 scan is reproducible")
+    x8 = rng.integers(-100, 100, 3_000_000).astype(np.int8)
+    assert_bits_equal(np.cumsum(gpu.array(x8)).get(), np.cumsum(x8), "int8 chained scan")
+    xu = rng.integers(0, 60000, 3_000_000).astype(np.uint16)
+    assert_bits_equal(np.cumsum(gpu.array(xu)).get(), np.cumsum(xu), "uint16 chained scan")
+    # a view that starts 4 bytes into the allocation is not 16-byte aligned: first-generation path
+    xi = rng.integers(-1000, 1000, (1 << 21) + 1).astype(np.int32)
+    assert_bits_equal(np.cumsum(gpu.array(xi)[1:]).get(), np.cumsum(xi[1:]), "unaligned 1-d scan")
+    for shape in ((64, 1024), (300, 4100), (1000, 20480), (70, 65536 + 64)):
+        mi = rng.integers(-100, 100, shape).astype(np.int32)
+        assert_bits_equal(np.cumsum(gpu.array(mi), axis=1).get(), np.cumsum(mi, axis=1), f"row scan int32 {shape}")
+        assert engine.last_kernel_name().endswith("_rowscan2"), engine.last_kernel_name()
+        md = rng.standard_normal(shape)
+        np.testing.assert_allclose(np.cumsum(gpu.array(md), axis=1).get(), np.cumsum(md, axis=1), rtol=1e-11, atol=1e-9)
+        mf = rng.random(shape).astype(np.float32)
+        np.testing.assert_allclose(np.cumsum(gpu.array(mf), axis=1).get(), np.cumsum(mf.astype(np.float64), axis=1),
+                                   rtol=1e-5)
+        mb = rng.integers(0, 2, shape).astype(bool)
+        assert_bits_equal(np.cumsum(gpu.array(mb), axis=1).get(), np.cumsum(mb, axis=1), f"row scan bool {shape}")
