@@ -298,3 +298,58 @@ def test_numpy_surface_shapes_and_dtypes_match_numpy_without_a_device():
     out = subprocess.run([sys.executable, tool, "--n", "150"], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     assert out.stdout.strip().splitlines()[-1].startswith("fuzz_shapes: 0 failing"), out.stdout[-3000:]
+
+
+def test_tile_family_for_transposed_operands_and_generation2_scans():
+    """Planning of the section 8(f) kernels added in round 2 (compile-only): a transposed operand
+    beside row-major ones selects the shared-memory tile family (two elements per thread when
+    every access is 8-byte aligned), in-place and reduced regions keep the strided kernel; 1-d
+    cumsum takes the one-pass chained scan, row scans the vectorised kernel."""
+    import delayrepay_b200 as dr
+    from delayrepay_b200 import engine, planner
+
+    def launches(fn):
+        n0 = len(engine.dry_log)
+        r = fn()
+        if hasattr(r, "run"):
+            r.run()
+        return engine.dry_log[n0:]
+
+    with engine.dry_run():
+        X = dr.array(np.ones((256, 320), np.float32))
+        Y = dr.array(np.ones((320, 256), np.float32))
+        (k, grid, threads), = launches(lambda: (Y.T + X) * 2.0)
+        assert k.name.startswith("dr_tile_") and threads == 256 and grid == 4 * 5
+        assert "tile0[64][65]" in k.source and "dr_ld<true, float, 2>" in k.source, "64 x 64 tile, pairs"
+        (k, _, _), = launches(lambda: Y.T[:, 1:] + X[:, 1:])
+        assert k.name.startswith("dr_tile_") and "dr_ld<true, float, 2>" not in k.source, "misaligned rows: W = 1"
+        D = dr.array(np.ones((100, 70)))
+        E = dr.array(np.ones((70, 100)))
+        v = dr.array(np.ones(70))
+        (k, _, _), = launches(lambda: np.exp(E.T) - D * v)
+        assert k.name.startswith("dr_tile_") and "tile0[32][33]" in k.source, "8-byte words: 32 x 32 tile"
+        (k, _, _), = launches(lambda: Y.T.copy())
+        assert k.name.startswith("dr_tile_"), "a 2-d transpose copy is a one-operand tile region"
+        small = dr.array(np.ones((16, 320), np.float32))
+        assert not launches(lambda: small.T + dr.array(np.ones((320, 16), np.float32)))[0][0].name.startswith("dr_tile_")
+        assert all(not k.name.startswith("dr_tile_") for k, _, _ in launches(lambda: np.sum(Y.T + X)))
+        # the class table itself
+        prog = planner.build_program([Y.T + X])
+        from delayrepay_b200.device import DeviceArray
+        out = DeviceArray.empty((256, 320), np.float32)
+        lay = planner.resolve_layout(prog, [out])
+        assert lay.family == "nd" and planner.tile_classes(prog, [out], lay) == (("t", "v"), 64, 2)
+
+        x = dr.array(np.ones(1 << 23, np.float32))
+        names = [k.name for k, _, _ in launches(lambda: np.cumsum(x))]
+        assert len(names) == 1 and names[0].endswith("_chain"), names
+        (k, grid, threads), = launches(lambda: np.cumsum(x))
+        assert (grid, threads) == (148 * 2, 512), "two co-resident CTAs per SM"
+        assert "st.relaxed.gpu.global.b128" in k.source, "totals travel as single 16-byte records"
+        M = dr.array(np.ones((256, 2048), np.float32))
+        assert [k.name.split("_")[-1] for k, _, _ in launches(lambda: np.cumsum(M, axis=1))] == ["rowscan2"]
+        odd = dr.array(np.ones((256, 2050), np.float32))
+        assert [k.name.split("_")[-1] for k, _, _ in launches(lambda: np.cumsum(odd, axis=1))] == ["rowscan"], \
+            "rows that are not a multiple of 16 bytes keep the scalar row scan"
+        short = dr.array(np.ones(5000, np.float32))
+        assert all(not k.name.endswith("_chain") for k, _, _ in launches(lambda: np.cumsum(short)))
