@@ -1058,7 +1058,10 @@ __device__ __forceinline__ NAME_pair NAME_shfl(NAME_pair p, int o) {
   q.i = dr_shfl_xor(p.i, o);
   return q;
 }
-// inner == 1: block (blockIdx.y = row, blockIdx.x = chunk of the row) -> one pair per (row, chunk)
+// inner == 1: block (blockIdx.y = row, blockIdx.x = chunk of the row) -> one pair per (row, chunk).
+// 16-byte aligned chunks are read as 128-bit vectors with a 32-bit running index and a two-
+// predicate test per element (strict, so the first of equal values wins; nan beats everything
+// once and is never beaten); the ragged rest goes through the general pair comparison.
 extern "C" __global__ void __launch_bounds__(256) NAME_rows(const T* __restrict__ in,
     T* __restrict__ pv, i64* __restrict__ pi, i64 n, i64 chunk) {
   __shared__ T sv[8];
@@ -1066,8 +1069,26 @@ extern "C" __global__ void __launch_bounds__(256) NAME_rows(const T* __restrict_
   const i64 row = blockIdx.y, lo = (i64)blockIdx.x * chunk, hi = lo + chunk < n ? lo + chunk : n;
   const T* p = in + row * n;
   NAME_pair best; best.v = (T)0; best.i = -1;
+  constexpr int V = 16 / (int)sizeof(T);
+  i64 k0 = lo;
+  if ((reinterpret_cast<unsigned long long>(p + lo) & 15ull) == 0ull) {
+    const int nvec = (int)((hi - lo) / V);
+    T bv = (T)0;
+    int bi = -1;
 #pragma unroll 4
-  for (i64 k = lo + threadIdx.x; k < hi; k += 256) {
+    for (int q = threadIdx.x; q < nvec; q += 256) {
+      const Vec<T, V> x = dr_ld<true, T, V>(p + lo + (i64)q * V);
+#pragma unroll
+      for (int e = 0; e < V; ++e) {
+        const T c = x.v[e];
+        const bool wins = !(ISMAX ? c <= bv : c >= bv) && !NAME_isnan(bv);
+        if (bi < 0 || wins) { bv = c; bi = q * V + e; }
+      }
+    }
+    if (bi >= 0) { best.v = bv; best.i = lo + bi; }
+    k0 = lo + (i64)nvec * V;
+  }
+  for (i64 k = k0 + threadIdx.x; k < hi; k += 256) {
     NAME_pair c; c.v = p[k]; c.i = k;
     if (NAME_beats(c, best)) best = c;
   }
@@ -1079,6 +1100,26 @@ extern "C" __global__ void __launch_bounds__(256) NAME_rows(const T* __restrict_
     for (int w = 1; w < 8; ++w) { NAME_pair q; q.v = sv[w]; q.i = si[w]; if (NAME_beats(q, best)) best = q; }
     pv[row * gridDim.x + blockIdx.x] = best.v;
     pi[row * gridDim.x + blockIdx.x] = best.i;
+  }
+}
+// fold many partial pairs of ONE output element per block (inner == 1, parts large)
+extern "C" __global__ void __launch_bounds__(256) NAME_finalb(const T* __restrict__ pv,
+    const i64* __restrict__ pi, i64* __restrict__ out, i64 parts) {
+  __shared__ T sv[8];
+  __shared__ i64 si[8];
+  const i64 o = blockIdx.x;
+  NAME_pair best; best.v = (T)0; best.i = -1;
+  for (i64 s = threadIdx.x; s < parts; s += 256) {
+    NAME_pair q; q.v = pv[o * parts + s]; q.i = pi[o * parts + s];
+    if (NAME_beats(q, best)) best = q;
+  }
+#pragma unroll
+  for (int w = 16; w > 0; w >>= 1) { const NAME_pair q = NAME_shfl(best, w); if (NAME_beats(q, best)) best = q; }
+  if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = best.v; si[threadIdx.x >> 5] = best.i; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) { NAME_pair q; q.v = sv[w]; q.i = si[w]; if (NAME_beats(q, best)) best = q; }
+    out[o] = best.i;
   }
 }
 // inner > 1: one thread per (outer, inner) element and chunk of n (blockIdx.y), coalesced along inner
@@ -1119,15 +1160,14 @@ extern "C" __global__ void __launch_bounds__(256) NAME_final(const T* __restrict
 def _arg_kernels(dt, is_max):
     key = ("arg", np.dtype(dt).str, bool(is_max))
     if key + ("rows",) in engine._kernels:
-        return {s: engine._kernels[key + (s,)] for s in ("rows", "cols", "final")}
+        return {s: engine._kernels[key + (s,)] for s in ("rows", "cols", "final", "finalb")}
     name = engine.kernel_name(key)
     T = ctype(dt) if np.dtype(dt) != np.dtype(bool) else "unsigned char"
-    src = _ARG_SRC.replace("NAME", name).replace("ISMAX", "1" if is_max else "0")
-    src = src.replace("(T)0", f"({T})0").replace("const T*", f"const {T}*").replace("T* ", f"{T}* ") \
-        .replace("T v;", f"{T} v;").replace("(T x)", f"({T} x)").replace("__shared__ T ", f"__shared__ {T} ")
+    # the element type is a macro: this text follows the prelude, whose templates are already parsed
+    src = f"#define T {T}\n" + _ARG_SRC.replace("NAME", name).replace("ISMAX", "1" if is_max else "0")
     _, cubin = engine.compile_source(name, src)
     out = {}
-    for suffix in ("rows", "cols", "final"):
+    for suffix in ("rows", "cols", "final", "finalb"):
         out[suffix] = engine._kernels[key + (suffix,)] = engine.Kernel(f"{name}_{suffix}", src, cubin, {})
     return out
 
@@ -1153,7 +1193,7 @@ def argreduce(src, axis, is_max):
     target = 148 * 8
     if inner == 1:
         parts = max(1, min(-(-target // outer), -(-n // 1024), 65535 if outer > 1 else 1 << 20))
-        chunk = -(-n // parts)
+        chunk = -(-(-(-n // parts)) // 1024) * 1024          # whole vectors per chunk; the index inside fits 32 bits
         parts = -(-n // chunk)
         rows_y = outer
         if rows_y > 65535:                      # grid.y limit: fall back to the column kernel
@@ -1177,6 +1217,10 @@ def argreduce(src, axis, is_max):
         pi = DeviceArray.empty((outer, parts, inner), np.int64, dev if dev >= 0 else None)
         a = Args(); a.ptr(src.ptr); a.ptr(pv.ptr); a.ptr(pi.ptr); a.i64(outer); a.i64(n); a.i64(inner); a.i64(chunk)
         launch(ks["cols"], dev, (min(blocks_x, 148 * 16), parts, 1), 256, a)
+    if inner == 1 and parts >= 64 and outer <= 65535:
+        a = Args(); a.ptr(pv.ptr); a.ptr(pi.ptr); a.ptr(out.ptr); a.i64(parts)
+        launch(ks["finalb"], dev, outer, 256, a)
+        return out
     a = Args(); a.ptr(pv.ptr); a.ptr(pi.ptr); a.ptr(out.ptr); a.i64(outer); a.i64(parts); a.i64(inner)
     launch(ks["final"], dev, _grid(outer * inner), 256, a)
     return out

@@ -50,7 +50,7 @@ for dt, w in ((np.float32, 4), (np.float64, 8)):
     report(f"X @ v {t}", N * w, lambda: (X @ v).run())
     report(f"v @ X {t}", N * w, lambda: (v @ X).run())
     report(f"var(X, axis=0) {t}", 2 * N * w, lambda: np.var(X, axis=0).run())
-    report(f"argmax(big) {t}", 2 * N * w, lambda: np.argmax(big).run())
+    report(f"argmax(big) {t}", N * w, lambda: np.argmax(big).run())
     report(f"cumsum(big) {t}", 2 * N * w, lambda: np.cumsum(big).run())
     report(f"cumsum(X, axis=0) {t}", 2 * N * w, lambda: np.cumsum(X, axis=0).run())
     report(f"cumsum(X, axis=1) {t}", 2 * N * w, lambda: np.cumsum(X, axis=1).run())
