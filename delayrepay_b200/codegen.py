@@ -159,7 +159,12 @@ def emit_expr(op, loop, out_dt, args, arg_dts, fast=False, relaxed=False, pow_mo
             else f"dr_{op}({a[0]}, {a[1]})"
     if op in _CALL2_RENAMED:
         fn = _CALL2_RENAMED[op]
-        return f"dr_{fn}({a[0]}, {a[1]})" if fn == "atan2" else f"dr_{fn}<{T}>({a[0]}, {a[1]})"
+        if fn == "atan2":
+            return f"dr_{fn}({a[0]}, {a[1]})"
+        # np.maximum / np.minimum return the SECOND operand when the two compare equal (their
+        # loops are `a > b ? a : b` with nan fix-ups), which is visible for -0.0 against +0.0;
+        # dr_max(x, y) = (x >= y || x != x) ? x : y keeps its first, hence the swapped operands
+        return f"dr_{fn}<{T}>({a[1]}, {a[0]})"
     raise KeyError(op)
 
 

@@ -1030,6 +1030,8 @@ class Scalar(NumpyEx):
     def _memo_key(cls, val):
         if val != val:
             return None
+        if val == 0 and isinstance(val, (float, np.floating)):
+            return ("Scalar", type(val).__name__, val, bool(np.signbit(val)))    # -0.0 == 0.0, but not the same operand
         return ("Scalar", type(val).__name__, val)
 
     def __hash__(self):
@@ -1254,6 +1256,14 @@ def clip(a, a_min=None, a_max=None, **kw):
     a_max = kw.pop("max", a_max) if a_max is None else a_max
     _no_extra("clip", kw)
     res = arg_to_numpy_ex(a)
+    # Which operand survives when `a` EQUALS a bound is visible for -0.0 against +0.0.  NumPy:
+    # two scalar bounds -> `a` (its constant-bounds loop); anything else -> the bound (one bound:
+    # np.maximum / np.minimum; array bounds: min(max(x, lo), hi)).  np.maximum / np.minimum keep
+    # their second operand.
+    def is_scalar(b):
+        return not isinstance(b, DelayArray) and np.ndim(b) == 0
+    if a_min is not None and a_max is not None and is_scalar(a_min) and is_scalar(a_max):
+        return np.minimum(a_max, np.maximum(a_min, res))
     if a_min is not None:
         res = np.maximum(res, a_min)
     if a_max is not None:

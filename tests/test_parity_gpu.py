@@ -1017,3 +1017,37 @@ def test_generation2_scans(gpu):
                                    rtol=1e-5)
         mb = rng.integers(0, 2, shape).astype(bool)
         assert_bits_equal(np.cumsum(gpu.array(mb), axis=1).get(), np.cumsum(mb, axis=1), f"row scan bool {shape}")
+
+
+def test_signed_zeros_of_maximum_minimum_clip_follow_numpy(gpu):
+    """np.maximum / np.minimum return their SECOND operand when the two compare equal and np.clip
+    depends on the kind of bound: only visible for -0.0 against +0.0 (found by fuzz seeds 7141,
+    7884 and 8132).  np.fmax / np.fmin are not pinned: NumPy's vector body returns the second
+    operand and its scalar tail the first, so the sign depends on the element's position."""
+    for dt in (np.float32, np.float64):
+        a = np.array([-0.0, 0.0, -0.0, 0.0, np.nan, 1.0, -0.0, 2.0] * 33, dt)
+        b = np.array([0.0, -0.0, -0.0, 0.0, 0.0, np.nan, 1.0, 2.0] * 33, dt)
+        A, B = gpu.array(a), gpu.array(b)
+        for name in ("maximum", "minimum", "fmax", "fmin"):
+            fn = getattr(np, name)
+            for x, y, X, Y in ((a, b, A, B), (b, a, B, A)):
+                got, want = fn(X, Y).get(), fn(x, y)
+                assert np.array_equal(got, want, equal_nan=True), name
+                if name[0] == "f":
+                    continue        # NumPy's own fmax / fmin differ between their SIMD body and scalar tail
+                ok = ~np.isnan(want)
+                assert np.array_equal(np.signbit(got[ok]), np.signbit(want[ok])), (name, np.dtype(dt).name)
+            if name[0] != "f":
+                got, want = fn(A, dt(0.0)).get(), fn(a, dt(0.0))
+                assert np.array_equal(np.signbit(got[~np.isnan(want)]), np.signbit(want[~np.isnan(want)])), (name, "scalar")
+        one = np.ones_like(a)
+        ONE = gpu.array(one)
+        for lo, hi, LO, HI in ((dt(0.0), dt(1.0), dt(0.0), dt(1.0)), (dt(-0.0), dt(0.0), dt(-0.0), dt(0.0)),
+                               (b, one, B, ONE), (-one, b, -ONE, B),
+                               (b, None, B, None), (None, b, None, B), (None, dt(-0.0), None, dt(-0.0)),
+                               (None, dt(0.0), None, dt(0.0)), (dt(-0.0), None, dt(-0.0), None),
+                               (dt(0.0), None, dt(0.0), None), (dt(0.0), one, dt(0.0), ONE), (b, dt(1.0), B, dt(1.0))):
+            got, want = np.clip(A, LO, HI).get(), np.clip(a, lo, hi)
+            assert np.array_equal(got, want, equal_nan=True)
+            ok = ~np.isnan(want)
+            assert np.array_equal(np.signbit(got[ok]), np.signbit(want[ok])), ("clip", np.dtype(dt).name, type(lo), type(hi))

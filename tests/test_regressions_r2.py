@@ -87,3 +87,14 @@ def test_complex_parts_of_fft_results(gpu):
     np.testing.assert_allclose(f.real.get(), want.real, atol=1e-9)
     np.testing.assert_allclose(f.imag.get(), want.imag, atol=1e-9)
     np.testing.assert_allclose(f.conj().get(), want.conj(), atol=1e-9)
+
+
+def test_negative_zero_scalar_is_not_hash_consed_with_positive_zero():
+    """-0.0 == 0.0 and hash(-0.0) == hash(0.0): the memo table used to hand back the Scalar node of
+    whichever zero was captured first (np.clip(x, -0.0, 0.0) then clipped to [+0.0, +0.0])."""
+    import numpy as np
+    import delayrepay_b200 as dr
+    for ty in (float, np.float32, np.float64):
+        p, n = dr.Scalar(ty(0.0)), dr.Scalar(ty(-0.0))
+        assert p is not n and not np.signbit(p.val) and np.signbit(n.val)
+        assert dr.Scalar(ty(-0.0)) is n and dr.Scalar(ty(0.0)) is p

@@ -322,6 +322,8 @@ def run_one(seed, verbose=False, dry=False):
             # nan payloads / signs may differ legitimately: compare with nan-equality
             # (the sign and payload of a nan are the platform's: x86 0/0 is -nan, CUDA's +nan)
             ok = ~np.isnan(want)
+            if "fmax(" in desc or "fmin(" in desc:
+                ok &= want != 0         # NumPy's fmax/fmin: SIMD body and scalar tail disagree on -0 vs +0
             same = np.array_equal(got, want, equal_nan=True) and \
                 np.array_equal(np.signbit(got[ok]), np.signbit(want[ok])) if want.dtype.kind == "f" else False
             if not same:
@@ -345,6 +347,14 @@ def run_one(seed, verbose=False, dry=False):
             mpmath.mp.prec = 200
             truth = np.array([float(mpmath.erfc(mpmath.mpf(float(v)))) for v in x[idx]]).astype(want.dtype)
             u, lim = ulps(g[idx], truth), 6.0
+        if u > lim and want.dtype == np.float32 and p.expr[0] == "un":
+            # NumPy's float32 loops (SVML) are themselves up to ~3 ulp from the truth for a few
+            # functions (arcsin near 0.95): judge against the float64 evaluation, rounded once
+            with np.errstate(all="ignore"):
+                x = np.asarray(ev(p.expr[2], [view(b, r) for b, r in p.leaves]))
+                truth = np.asarray(ev(("un", p.expr[1], ("sc", x.astype(np.float64))), []))
+            truth = np.broadcast_to(truth, want.shape).astype(np.float32)
+            u, lim = ulps(got, truth), 1.0
         if u > lim:
             return f"VALUE(ulp) ulps={u:.3g} | {desc}"
         return None
