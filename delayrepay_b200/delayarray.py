@@ -1062,7 +1062,7 @@ def arg_to_numpy_ex(arg):
     """[delayarray.py:470-479]"""
     if isinstance(arg, DelayArray):
         return arg
-    if isinstance(arg, Number):
+    if isinstance(arg, (Number, np.generic)):        # np.bool_ is a NumPy scalar but not a numbers.Number
         return Scalar(arg)
     if _backend.is_ndarray(arg) or isinstance(arg, np.ndarray):
         return NPArray(arg)

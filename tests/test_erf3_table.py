@@ -27,8 +27,8 @@ def _fma(a, b, c):
 
 
 def _erf3(x, words, mask, shift, sqrt_err_ulp=0.0):
-    magic = f32(49152.0)
-    ap = np.minimum(np.abs(x) * f32(0.25), f32(1.0)).astype(f32)                  # FMUL.SAT
+    magic = f32(98304.0)
+    ap = np.minimum(np.abs(x), f32(4.0)).astype(f32)                              # FMNMX (exact, also for subnormals)
     s = (np.sqrt(ap.astype(np.float64)).astype(f32) * f32(1 + sqrt_err_ulp * 2.0 ** -23)).astype(f32)   # MUFU.SQRT
     row = (s + magic).astype(f32).view(np.int32) - magic.view(np.int32)           # FADD, LEA
     w = words[row]
@@ -45,6 +45,7 @@ def test_shipped_erf3_table_is_within_its_error_bound():
     assert words.shape == (257, 4) and mask == 0xFFFFF800 and shift == 21
     rng = np.random.default_rng(0)
     x = np.concatenate([rng.uniform(-6, 6, 1 << 18), 10.0 ** rng.uniform(-30, 0.7, 1 << 18),
+                        10.0 ** rng.uniform(-45.5, -30, 1 << 16),              # subnormal arguments and results
                         np.linspace(0, 4.1, (1 << 18) + 1), np.linspace(0, 2.0 ** -8, 1 << 16),
                         (np.arange(0, 258) / 256.0) ** 2 * 4, ((np.arange(0, 258) + 0.5) / 256.0) ** 2 * 4]).astype(f32)
     truth = erf(x.astype(np.float64))

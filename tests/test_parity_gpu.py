@@ -257,6 +257,7 @@ def test_generation3_erf_in_staged_kernels(gpu):
         x = (np.exp(rng.uniform(-60, 2.5, n)) * rng.choice([-1.0, 1.0], n)).astype(np.float32)
         x = np.concatenate([x, np.linspace(-6, 6, n // 2, dtype=np.float32),
                             rng.uniform(-2.0 ** -7, 2.0 ** -7, n // 4).astype(np.float32),
+                            (10.0 ** rng.uniform(-45.5, -30, n // 4) * rng.choice([-1.0, 1.0], n // 4)).astype(np.float32),
                             ((np.arange(0, 260, dtype=np.float64) / 256.0) ** 2 * 4).astype(np.float32),      # row centres
                             (((np.arange(0, 260, dtype=np.float64) + 0.5) / 256.0) ** 2 * 4).astype(np.float32),  # row borders
                             np.array([0.0, -0.0, 1e-45, -1e-45, 4.0, 3.9999998, 4.0000005, 1e30, -1e30, np.inf, -np.inf,

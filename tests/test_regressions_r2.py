@@ -98,3 +98,17 @@ def test_negative_zero_scalar_is_not_hash_consed_with_positive_zero():
         p, n = dr.Scalar(ty(0.0)), dr.Scalar(ty(-0.0))
         assert p is not n and not np.signbit(p.val) and np.signbit(n.val)
         assert dr.Scalar(ty(-0.0)) is n and dr.Scalar(ty(0.0)) is p
+
+
+def test_numpy_bool_scalar_operands_are_captured():
+    """np.True_ is not a numbers.Number: `np.where(np.less_equal(-3, -3), x, y)` raised
+    NotImplementedError (fuzz seed 20358)."""
+    import numpy as np
+    import delayrepay_b200 as dr
+    from delayrepay_b200 import engine
+    with engine.dry_run():
+        x = dr.array(np.ones(8, np.float32))
+        r = np.where(np.less_equal(-3, -3), x, x * 2)
+        assert isinstance(r, dr.DelayArray) and r.dtype == np.float32 and r.shape == (8,)
+        r.run()
+        assert (x * np.True_).dtype == np.float32 and (x + np.bool_(False)).shape == (8,)
