@@ -474,7 +474,8 @@ def _scan_kernels(in_dt, acc_dt):
 
 # 2 CTAs of 512 threads per SM; totals are published one round ahead.  Measured alternatives
 # (profiles/r2_scan_chain_experiments.txt): 1024 x 1 and 256 x 4 are within 2 %, 2 or 3 rounds
-# ahead are 5 - 8 % slower (the second read starts to miss L2)
+# ahead are 5 - 8 % slower (the second read starts to miss L2), smaller tiles (8 or 4 elements per
+# thread with 3 or 4 CTAs per SM) are 30 - 100 % slower: the cost is per round
 _CHAIN_THREADS, _CHAIN_CPS, _CHAIN_SLACK = 512, 2, 1
 
 
