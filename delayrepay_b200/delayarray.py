@@ -128,6 +128,18 @@ def _layout_of(arr):
 
 
 # --------------------------------------------------------------------------- DelayArray
+_BASIC_INDEX = (slice, int, np.integer, type(None), type(Ellipsis))
+
+
+def _is_basic_index(key):
+    if isinstance(key, tuple):
+        for k in key:                    # (the builtin `all` is shadowed by the np.all handler below)
+            if not isinstance(k, _BASIC_INDEX):
+                return False
+        return True
+    return isinstance(key, _BASIC_INDEX)
+
+
 class DelayArray(numpy.lib.mixins.NDArrayOperatorsMixin):
     """Lazy array: NumPy calls on it build graph nodes; see module docstring."""
 
@@ -290,11 +302,9 @@ class DelayArray(numpy.lib.mixins.NDArrayOperatorsMixin):
             if hit is not None:
                 return hit
         got = self._getitem(key)
-        if self.kind == "leaf" and got.kind == "leaf":
-            try:
-                hash(key)
-            except TypeError:
-                return got
+        # only BASIC indices make views; a gather or a mask compaction is a copy of the data as
+        # it is now and must be taken again next time
+        if self.kind == "leaf" and got.kind == "leaf" and _is_basic_index(key):
             if views is None:
                 views = self._views = {}
             elif len(views) >= 64:

@@ -1052,3 +1052,23 @@ def test_signed_zeros_of_maximum_minimum_clip_follow_numpy(gpu):
             assert np.array_equal(got, want, equal_nan=True)
             ok = ~np.isnan(want)
             assert np.array_equal(np.signbit(got[ok]), np.signbit(want[ok])), ("clip", np.dtype(dt).name, type(lo), type(hi))
+
+
+def test_row_gather_in_128_bit_words(gpu):
+    """X[rows] with rows of a multiple of 16 bytes takes the vector gather (extras._TAKE16_SRC)."""
+    from delayrepay_b200 import engine
+    rng = np.random.default_rng(303)
+    for dt, shape in ((np.float32, (300, 64)), (np.float64, (50, 12)), (np.int8, (40, 64)), (np.float32, (7, 5, 4, 8)),
+                      (np.int64, (1000, 2, 8))):
+        h = (rng.standard_normal(shape) * 100).astype(dt)
+        d = gpu.array(h)
+        for idx in (rng.integers(-shape[0], shape[0], 257), rng.integers(0, shape[0], (3, 40)).astype(np.int32),
+                    np.array([shape[0] - 1, 0, -1, -shape[0]])):
+            got = d[gpu.array(idx)].get()
+            assert engine.last_kernel_name().startswith("dr_take16_"), engine.last_kernel_name()
+            assert got.shape == h[idx].shape and np.array_equal(got, h[idx]), (dt, shape)
+        assert np.array_equal(d[1:][gpu.array(np.array([0, 5, 2]))].get(), h[1:][[0, 5, 2]])
+    odd = gpu.array(np.arange(60, dtype=np.float32).reshape(10, 6))          # 24-byte rows: scalar gather
+    assert np.array_equal(odd[gpu.array(np.array([3, 3, 0]))].get(), np.arange(60, dtype=np.float32).reshape(10, 6)[[3, 3, 0]])
+    with pytest.raises(IndexError):
+        gpu.array(np.zeros((10, 64), np.float32))[gpu.array(np.array([10]))]

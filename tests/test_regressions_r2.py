@@ -112,3 +112,19 @@ def test_numpy_bool_scalar_operands_are_captured():
         assert isinstance(r, dr.DelayArray) and r.dtype == np.float32 and r.shape == (8,)
         r.run()
         assert (x * np.True_).dtype == np.float32 and (x + np.bool_(False)).shape == (8,)
+
+
+@pytest.mark.gpu
+def test_gather_and_mask_results_are_not_cached_as_views(gpu):
+    """The per-leaf view cache (round 2) also kept the RESULT of `a[idx]` / `a[mask]` under the
+    index object: the second `a[idx]` after a write to `a` returned the stale copy."""
+    import numpy as np
+    h = np.arange(40, dtype=np.float32).reshape(10, 4)
+    a = gpu.array(h.copy())
+    idx = gpu.array(np.array([1, 3, 3, 0]))
+    mask = gpu.array(h[:, 0] > 10)
+    first, firstm = a[idx].get(), a[mask].get()
+    a[...] = a * 2.0
+    assert np.array_equal(first, h[[1, 3, 3, 0]]) and np.array_equal(a[idx].get(), 2 * h[[1, 3, 3, 0]])
+    assert np.array_equal(firstm, h[h[:, 0] > 10]) and np.array_equal(a[mask].get(), 2 * h[h[:, 0] > 10])
+    assert a[2:5] is a[2:5] and a[1, None] is a[1, None]          # basic indices still share one view node
