@@ -313,8 +313,8 @@ def tile_classes(prog, outs, lay):
             cls.append("b")
         elif st[1] == item:
             cls.append("v")
-        elif st[0] == item and item in (4, 8):
-            cls.append("t")
+        elif st[0] == item and item in (4, 8) and abs(st[1]) >= item:
+            cls.append("t")             # (a column vector, stride 0 along C, is a plain broadcast load)
             staged.append(item)
         else:
             cls.append("s")
