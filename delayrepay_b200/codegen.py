@@ -1128,11 +1128,16 @@ def gen_cols(name, prog, in_class, reduce, threads=256, V=1, partial=False):
     w(f"    const i64 o = idx / nvec, c = (idx - o * nvec) * {V};")
     w(f"    {A} acc[{V}];")
     w(f"#pragma unroll\n    for (int e = 0; e < {V}; ++e) acc[e] = {ident};")
-    w("#pragma unroll 4\n    for (i64 r = r0; r < r1; ++r) {")
+    # 8-byte operands: sixteen trips in flight through the non-coherent path (measured on 16384^2
+    # float64: sum(X, axis=0) 5.7 -> 6.1 TB/s, v @ X 4.2 -> 5.4; float32 measured indifferent to both,
+    # profiles/r2_cols_family_sweep.txt)
+    wide = any(a.dtype.itemsize == 8 and c == "v" for a, c in zip(arrays, in_class))
+    unroll, stream = (16, "true") if wide else (4, "false")
+    w(f"#pragma unroll {unroll}\n    for (i64 r = r0; r < r1; ++r) {{")
     for i, (a, c) in enumerate(zip(arrays, in_class)):
         T = ctype(a.dtype)
         if c == "v":
-            w(f"      const Vec<{T}, {V}> vx{i} = dr_ld<false, {T}, {V}>(reinterpret_cast<const {T}*>"
+            w(f"      const Vec<{T}, {V}> vx{i} = dr_ld<{stream}, {T}, {V}>(reinterpret_cast<const {T}*>"
               f"(in{i} + o * g.so[{i}] + r * g.sr[{i}]) + c);")
         elif c == "i":
             w(f"      const {T} ix{i} = *reinterpret_cast<const {T}*>(in{i} + o * g.so[{i}] + r * g.sr[{i}]);")
