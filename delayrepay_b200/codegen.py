@@ -117,12 +117,19 @@ def emit_expr(op, loop, out_dt, args, arg_dts, fast=False, relaxed=False, pow_mo
         # (e.g. it widens `(double)(x * x * x)`): do the arithmetic in the unsigned type
         U = _UNSIGNED[loop[0].char]
         if op == "negative":
-            return f"(({O})(({U})0 - ({U}){a[0]}))"
+            # 0 - x with a zero the assembler cannot see (every launch has gridDim.z == 1): ptxas
+            # 12.9 folds a literal negation into the operands of a fused three-input integer
+            # min / max (VIMNMX3) and loses it for one of them -- min(-a, -b, -c) came back as
+            # min(a', -b, ...) for int32 / int16 (fuzz seed 60525; the SASS shows
+            # `VIMNMX3 R4, R3, R4, R15` with only R15 negated).  A real subtraction is one IADD3.
+            return f"(({O})(({U})(gridDim.z - 1u) - ({U}){a[0]}))"
         return f"(({O})(({U}){a[0]} {_INFIX[op]} ({U}){a[1]}))"
     if op in _INFIX:
         e = f"({a[0]} {_INFIX[op]} {a[1]})"
         return e if out_dt.kind == "b" else f"(({O}){e})"
     if op == "negative":
+        if k == "u":
+            return f"(({O})(({O})(gridDim.z - 1u) - {a[0]}))"        # as above
         return f"(({O})(-{a[0]}))"
     if op == "positive":
         return a[0]

@@ -330,7 +330,8 @@ def run_one(seed, verbose=False, dry=False):
     if want.dtype.kind in "biu":
         if p.kind == "trans" or not np.array_equal(got, want):
             if not np.array_equal(got, want):
-                return f"VALUE(int) mismatches={int((got != want).sum())} | {desc}"
+                return (f"VALUE(int) mismatches={int((got != want).sum())} got={got.ravel()[:3]} "
+                        f"want={want.ravel()[:3]} | {desc}")
         return None
     if p.kind == "arith":
         if got.tobytes() != want.tobytes():
@@ -383,7 +384,11 @@ def run_one(seed, verbose=False, dry=False):
             mag = ev(("un", "absolute", p.expr), [view(b, r) for b, r in p.leaves])
             mag = np.asarray(getattr(np, "sum" if p.root[0] != "prod" else "prod")(
                 mag, axis=p.root[1])) if p.root[0] != "mean" else np.asarray(np.mean(mag, axis=p.root[1]))
-        if p.root[0] == "prod" and not np.all(np.isfinite(mag)):
+        if p.root[0] == "prod":
+            with np.errstate(all="ignore"):         # the same, leaving exact zeros out (0 * inf)
+                nz = np.asarray(ev(("un", "absolute", p.expr), [view(b, r) for b, r in p.leaves])).astype(np.float64)
+                mag_nz = np.prod(np.where(nz == 0, 1.0, nz), axis=p.root[1])
+        if p.root[0] == "prod" and not (np.all(np.isfinite(mag)) and np.all(np.isfinite(mag_nz))):
             # the product of the magnitudes overflows: whether a partial product reaches inf before
             # it meets a zero (0 * inf = nan) depends on the ORDER of the multiplications, which a
             # parallel reduction does not share with NumPy's sequential loop
