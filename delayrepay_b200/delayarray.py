@@ -733,6 +733,15 @@ class WhereEx(NumpyEx):
         sig = [k.val if (isinstance(k, Scalar) and k.weak_type is not None) else k.dtype
                for k in (a, b)]
         out = np.result_type(*sig)
+        if out.kind in "iu":
+            # np.where casts a Python int that does not fit the result type with C semantics
+            # (np.where(c, uint8_array, -3) holds 253), where a ufunc would raise OverflowError
+            kids = []
+            for k in (a, b):
+                if isinstance(k, Scalar) and k.weak_type is int and not (np.iinfo(out).min <= k.val <= np.iinfo(out).max):
+                    k = Scalar(np.array(k.val).astype(out)[()])
+                kids.append(k)
+            self.children = [cond] + kids
         self.loop, self.dtype = (np.dtype(bool), out, out), out
         self.shape = np.broadcast_shapes(cond.shape, a.shape, b.shape)
         self._psig, self._pops = _plan_info(("where", self.loop, self.shape), self.children)

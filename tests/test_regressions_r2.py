@@ -128,3 +128,18 @@ def test_gather_and_mask_results_are_not_cached_as_views(gpu):
     assert np.array_equal(first, h[[1, 3, 3, 0]]) and np.array_equal(a[idx].get(), 2 * h[[1, 3, 3, 0]])
     assert np.array_equal(firstm, h[h[:, 0] > 10]) and np.array_equal(a[mask].get(), 2 * h[h[:, 0] > 10])
     assert a[2:5] is a[2:5] and a[1, None] is a[1, None]          # basic indices still share one view node
+
+
+def test_where_wraps_python_ints_that_do_not_fit_like_numpy():
+    """np.where(c, uint8_array, -3) holds 253 (fuzz seed 71979 raised OverflowError in the planner)."""
+    import numpy as np
+    import delayrepay_b200 as dr
+    from delayrepay_b200 import engine
+    with engine.dry_run():
+        x = dr.array(np.ones(8, np.uint8))
+        r = np.where(x > 0, x, -3)
+        assert r.dtype == np.uint8 and r.children[2].val == 253 and r.children[2].dtype == np.uint8
+        r.run()
+        y = np.where(dr.array(np.ones(8, np.int8)) > 0, 300, dr.array(np.ones(8, np.int8)))
+        assert y.dtype == np.int8 and y.children[1].val == 44
+        y.run()
