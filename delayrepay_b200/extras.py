@@ -159,11 +159,15 @@ extern "C" __global__ void __launch_bounds__(256) NAME_final(const TIN* __restri
 # local scan, a shuffle scan over the lanes and the running total of the earlier j.
 #
 # NAME_chain (1-d): G co-resident CTAs walk the tiles round by round (tile t = round * G + p).
-# A tile publishes its total (agg[t], flag[t]) as soon as its data is reduced, then waits for the
-# totals of the tiles in front of it IN ITS OWN ROUND and for the round's carry; the last tile of
-# a round publishes the next carry.  Nothing is read twice (8 B / element for float32 instead of
-# 12), the next tile's loads are in flight while a CTA waits, and — unlike decoupled look-back —
-# every prefix is the same fixed-order sum on every run: the result is reproducible bit for bit.
+# A CTA reads each of its tiles twice: one round AHEAD, from HBM, only to publish the tile's total
+# as a 16-byte {value, flag} record (single 128-bit relaxed store, no fence), and in its own round,
+# from L2, for the scan itself.  In between, the records of the whole round have long been
+# published: every thread fetches one of them (the look-back is one round trip to L2), the tiles
+# in front give the tile's prefix and all of them the next carry, which every CTA therefore
+# computes for itself.  HBM traffic stays 8 B / element for float32 (three-phase scan: 12), and —
+# unlike decoupled look-back — every prefix is the same fixed-order sum on every run: the result
+# is reproducible bit for bit.  All G CTAs must be resident at once (the host sizes G from the
+# occupancy query; a lost peer ends in a trap after ~10^8 polls, never in a hang).
 _SCAN2_SRC = r'''
 #define VE (16 / (int)sizeof(TIN))
 #define NV NVVAL
