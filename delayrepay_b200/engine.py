@@ -277,6 +277,8 @@ def launch(kernel, dev, grid, block, args, smem=0, stream=0, cluster=1):
         return
     blob, offs, n = args.pack()
     gx, gy, gz = (tuple(grid) + (1, 1))[:3] if not isinstance(grid, int) else (grid, 1, 1)
+    if gz != 1:                 # generated code uses gridDim.z - 1 as a zero ptxas cannot fold (codegen.emit_expr)
+        raise ValueError("kernels are launched with gridDim.z == 1")
     bx, by, bz = (tuple(block) + (1, 1))[:3] if not isinstance(block, int) else (block, 1, 1)
     check(lib.drc_launch_packed(dev, stream, kernel.func(dev), gx, gy, gz, bx, by, bz, smem,
                                 cluster, blob, offs, n))
