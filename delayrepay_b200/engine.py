@@ -354,8 +354,6 @@ def run_program(prog, outs, reduce=None, inplace=False):
         # a transposed operand among row-major ones (`X.T + X`): shared-memory tiles, every
         # global access coalesced
         cls, T, W = planner.tile_classes(prog, outs, lay)
-        if os.environ.get("DR_TILE_W"):
-            W = min(W, int(os.environ["DR_TILE_W"]))
         smem, threads, scl = 0, 256, None
         key = ("tile", prog.key(), cls, tuple(d.str for d in out_dts), T, W)
         kern = get_kernel(key, lambda name: codegen.gen_tile(name, prog, cls, out_dts, T=T, W=W))
