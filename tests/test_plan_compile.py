@@ -353,3 +353,33 @@ def test_tile_family_for_transposed_operands_and_generation2_scans():
             "rows that are not a multiple of 16 bytes keep the scalar row scan"
         short = dr.array(np.ones(5000, np.float32))
         assert all(not k.name.endswith("_chain") for k, _, _ in launches(lambda: np.cumsum(short)))
+
+
+def test_emission_rules_found_by_the_late_fuzz_batches():
+    """Compile-only guards for three round-2 emission rules: integer negation is a subtraction from
+    a zero ptxas cannot fold (it loses a literal negation inside a fused VIMNMX3), np.maximum /
+    np.minimum put their second operand first in dr_max / dr_min (NumPy returns the second operand
+    when the two compare equal), np.clip chooses the operand order by the kind of its bounds."""
+    import delayrepay_b200 as dr
+    from delayrepay_b200 import engine
+
+    def source(fn):
+        n0 = len(engine.dry_log)
+        fn().run()
+        return engine.dry_log[n0][0].source
+
+    with engine.dry_run():
+        xi = dr.array(np.arange(64, dtype=np.int32))
+        xu = dr.array(np.arange(64, dtype=np.uint16))
+        a = dr.array(np.ones(64, np.float64))
+        b = dr.array(np.ones(64, np.float64))
+        assert "(unsigned int)(gridDim.z - 1u) - (unsigned int)x0" in source(lambda: np.minimum(-xi, xi))
+        assert "(gridDim.z - 1u) - x0" in source(lambda: -xu + xu)
+        assert "dr_max<double>(x1, x0)" in source(lambda: np.maximum(a, b)), "second operand first"
+        assert "dr_min<double>(x1, x0)" in source(lambda: np.minimum(a, b))
+        s = source(lambda: np.clip(a, 0.0, 1.0))
+        assert "dr_max<double>(x0, s0)" in s and "dr_min<double>(t0, s1)" in s, "two scalar bounds keep `a` on equality"
+        s = source(lambda: np.clip(a, b, None))
+        assert "dr_max<double>(x1, x0)" in s, "an array bound wins on equality"
+        with pytest.raises(ValueError):
+            engine.launch(engine._kernels[next(iter(engine._kernels))], 0, (1, 1, 2), 32, engine.Args())
